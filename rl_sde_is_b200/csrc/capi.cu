@@ -1,0 +1,272 @@
+// C ABI of librlsde_b200.so (declared in include/rlsde.h): argument checking, host-side
+// precomputation of the environment constants the way torch / numpy round them, dispatch on the
+// policy shape, and stream-ordered launches.  No torch types, no exceptions, no global mutable state
+// except the thread-local text of the last CUDA error.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/rlsde.h"
+#include "aux_kernels.cuh"
+#include "rollout_bwd.cuh"
+
+namespace rlsde {
+
+static thread_local char g_last_cuda_error[256] = "";
+
+static int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", where, cudaGetErrorString(e));
+  return RLSDE_ERR_CUDA;
+}
+
+// shapes with compiled fused kernels: X(d, H)
+// (H = 64 compiles, but takes > 6 min per shape in the front end; it is left out of the default build)
+#define RLSDE_SHAPES(X) X(1, 32) X(2, 32) X(3, 32) X(4, 32) X(10, 32)
+
+static bool shape_supported(int d, int H, int n_hidden) {
+  if (n_hidden != 2) return false;
+#define X(D_, H_) if (d == D_ && H == H_) return true;
+  RLSDE_SHAPES(X)
+#undef X
+  return false;
+}
+
+static int device_sm_count(int* sm_count) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { cuda_fail(e, "cudaGetDevice"); return RLSDE_ERR_NO_DEVICE; }
+  int n = 0;
+  e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) { cuda_fail(e, "cudaDeviceGetAttribute"); return RLSDE_ERR_NO_DEVICE; }
+  *sm_count = n;
+  return RLSDE_OK;
+}
+
+static int check_env_mlp(const rlsde_env* env, const rlsde_mlp* mlp) {
+  if (!env || !mlp) return RLSDE_ERR_INVALID_ARG;
+  if (env->d < 1 || env->d > RLSDE_MAX_D) return RLSDE_ERR_INVALID_ARG;
+  if (mlp->d_in != env->d || mlp->d_out != env->d) return RLSDE_ERR_INVALID_ARG;
+  if (!(env->dt > 0) || !(env->sigma > 0)) return RLSDE_ERR_INVALID_ARG;
+  if (env->hit_rule != RLSDE_HIT_ALL_GE_LB && env->hit_rule != RLSDE_HIT_X0_IN_LB_RB) return RLSDE_ERR_INVALID_ARG;
+  if (!shape_supported(env->d, mlp->d_hidden, mlp->n_hidden)) return RLSDE_ERR_UNSUPPORTED;
+  return RLSDE_OK;
+}
+
+static void fill_env(const rlsde_env* env, FwdArgs& A) {
+  for (int i = 0; i < RLSDE_MAX_D; ++i) {
+    const double al = i < env->d ? env->alpha[i] : 0.0;
+    A.c4a_d[i] = 4.0 * al;
+    A.c4a_f[i] = (float)(4.0 * al);   // torch multiplies the f32 state by the python scalar 4*alpha cast to f32
+    A.x0_d[i] = i < env->d ? (double)(float)env->x0[i] : 0.0;   // state_init is float32 (environments.py:30)
+    A.x0_f[i] = i < env->d ? (float)env->x0[i] : 0.f;
+  }
+  A.sigma_d = env->sigma; A.sigma_f = (float)env->sigma;   // sigma_tensor / dt_tensor are float32 (environments.py:19,23)
+  A.dt_d = env->dt; A.dt_f = (float)env->dt;
+  A.lb_d = env->lb; A.rb_d = env->rb; A.lb_f = (float)env->lb; A.rb_f = (float)env->rb;
+  A.noise_scale2 = (float)(-2.0 * env->dt * 0.6931471805599453);
+  A.hit_rule = env->hit_rule;
+}
+
+static int fill_cfg(const rlsde_rollout_cfg* cfg, FwdArgs& A) {
+  if (!cfg || cfg->K < 0 || cfg->n_steps_lim < 1 || cfg->n_steps_lim > 2000000000LL) return RLSDE_ERR_INVALID_ARG;
+  if ((cfg->flags & RLSDE_F_NOISE_INJECTED) && cfg->noise_steps < 1) return RLSDE_ERR_INVALID_ARG;
+  if ((cfg->flags & RLSDE_F_STORE_PATH) && (cfg->ckpt_every < 1 || cfg->ckpt_stride < 1)) return RLSDE_ERR_INVALID_ARG;
+  A.K = cfg->K; A.traj_offset = cfg->traj_offset;
+  A.K_global = cfg->K_global > 0 ? cfg->K_global : cfg->K;
+  A.seed = cfg->seed; A.n_steps_lim = cfg->n_steps_lim; A.noise_steps = cfg->noise_steps;
+  A.flags = cfg->flags; A.ckpt_every = cfg->ckpt_every > 0 ? cfg->ckpt_every : 1; A.ckpt_stride = cfg->ckpt_stride;
+  A.n_grid = cfg->n_grid; A.grid_lo = cfg->grid_lo; A.grid_hi = cfg->grid_hi; A.grid_h = cfg->grid_h;
+  return RLSDE_OK;
+}
+
+// workspace layout: [0, 256) work counters; [256, ...) statistics partials
+constexpr size_t WS_COUNTER_BYTES = 256;
+constexpr size_t WS_STATS_BYTES = (size_t)STATS_BLOCKS * RLSDE_NSTATS * sizeof(double);
+
+}  // namespace rlsde
+
+using namespace rlsde;
+
+extern "C" {
+
+int rlsde_version(void) { return RLSDE_VERSION; }
+
+const char* rlsde_strerror(int status) {
+  switch (status) {
+    case RLSDE_OK: return "ok";
+    case RLSDE_ERR_INVALID_ARG: return "invalid argument";
+    case RLSDE_ERR_UNSUPPORTED: return "no fused kernel compiled for this policy shape (d, hidden width, depth)";
+    case RLSDE_ERR_CUDA: return "CUDA error (see rlsde_last_cuda_error)";
+    case RLSDE_ERR_NO_DEVICE: return "no usable CUDA device";
+    case RLSDE_ERR_WORKSPACE: return "workspace too small (see rlsde_workspace_bytes)";
+    default: return "unknown status";
+  }
+}
+
+const char* rlsde_last_cuda_error(void) { return g_last_cuda_error; }
+
+int rlsde_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { cuda_fail(e, "cudaGetDevice"); return RLSDE_ERR_NO_DEVICE; }
+  int n = 0, ma = 0, mi = 0;
+  if ((e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess ||
+      (e = cudaDeviceGetAttribute(&ma, cudaDevAttrComputeCapabilityMajor, dev)) != cudaSuccess ||
+      (e = cudaDeviceGetAttribute(&mi, cudaDevAttrComputeCapabilityMinor, dev)) != cudaSuccess) {
+    cuda_fail(e, "cudaDeviceGetAttribute");
+    return RLSDE_ERR_NO_DEVICE;
+  }
+  if (sm_count) *sm_count = n;
+  if (cc_major) *cc_major = ma;
+  if (cc_minor) *cc_minor = mi;
+  return RLSDE_OK;
+}
+
+int rlsde_supported(int32_t d, int32_t d_hidden, int32_t n_hidden) { return shape_supported(d, d_hidden, n_hidden) ? 1 : 0; }
+
+int64_t rlsde_param_count(const rlsde_mlp* mlp) {
+  if (!mlp) return -1;
+  const int64_t d = mlp->d_in, H = mlp->d_hidden, o = mlp->d_out;
+  return d * H + H + (int64_t)(mlp->n_hidden - 1) * (H * H + H) + H * o + o;
+}
+
+size_t rlsde_workspace_bytes(int64_t K) {
+  (void)K;
+  return WS_COUNTER_BYTES + WS_STATS_BYTES + bwd_workspace_bytes();
+}
+
+int rlsde_rollout_fwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* params_host,
+                      const rlsde_rollout_cfg* cfg, const float* noise_dev, const float* policy_opt_dev,
+                      void* G_dev, void* S_dev, int32_t* T_dev, void* l2_dev, void* logw_dev, float* path_dev,
+                      double* stats_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_env_mlp(env, mlp);
+  if (rc != RLSDE_OK) return rc;
+  if (!params_host || !G_dev || !S_dev || !T_dev || !workspace_dev) return RLSDE_ERR_INVALID_ARG;
+  if (workspace_bytes < WS_COUNTER_BYTES + WS_STATS_BYTES) return RLSDE_ERR_WORKSPACE;
+  FwdArgs A;
+  memset(&A, 0, sizeof(A));
+  fill_env(env, A);
+  if ((rc = fill_cfg(cfg, A)) != RLSDE_OK) return rc;
+  if ((A.flags & RLSDE_F_NOISE_INJECTED) && !noise_dev) return RLSDE_ERR_INVALID_ARG;
+  if ((A.flags & RLSDE_F_STORE_PATH) && !path_dev) return RLSDE_ERR_INVALID_ARG;
+  if (policy_opt_dev && (cfg->n_grid < 1 || !(cfg->grid_h > 0) || env->d != 1)) return RLSDE_ERR_INVALID_ARG;
+  A.noise = noise_dev; A.policy_opt = policy_opt_dev;
+  A.G = G_dev; A.S = S_dev; A.T = T_dev; A.l2 = l2_dev; A.logw = logw_dev; A.path = path_dev;
+  A.counter = (unsigned long long*)workspace_dev;
+  if (A.K == 0) return RLSDE_OK;
+  int sm = 0;
+  if ((rc = device_sm_count(&sm)) != RLSDE_OK) return rc;
+  cudaError_t e = cudaMemsetAsync(workspace_dev, 0, WS_COUNTER_BYTES, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+  int lrc = -1;
+#define X(D_, H_) if (env->d == D_ && mlp->d_hidden == H_) lrc = launch_rollout_fwd<D_, H_>(params_host, A, sm, stream);
+  RLSDE_SHAPES(X)
+#undef X
+  if (lrc != 0) return cuda_fail((cudaError_t)lrc, "rollout_fwd launch");
+  if (stats_dev) {
+    double* partial = (double*)((char*)workspace_dev + WS_COUNTER_BYTES);
+    lrc = launch_reduce_stats(A.K, A.n_steps_lim, (A.flags & RLSDE_F_STATE_F64) != 0, G_dev, S_dev, T_dev, l2_dev, logw_dev,
+                              stats_dev, partial, stream);
+    if (lrc != 0) return cuda_fail((cudaError_t)lrc, "reduce_stats launch");
+  }
+  return RLSDE_OK;
+}
+
+int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* params_host,
+                      const rlsde_rollout_cfg* cfg, const float* noise_dev, const float* G_dev, const int32_t* T_dev,
+                      const float* path_dev, double loss_scale, float* grad_dev, void* workspace_dev,
+                      size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_env_mlp(env, mlp);
+  if (rc != RLSDE_OK) return rc;
+  if (!params_host || !G_dev || !T_dev || !path_dev || !grad_dev || !workspace_dev) return RLSDE_ERR_INVALID_ARG;
+  if (workspace_bytes < rlsde_workspace_bytes(cfg ? cfg->K : 0)) return RLSDE_ERR_WORKSPACE;
+  FwdArgs A;
+  memset(&A, 0, sizeof(A));
+  fill_env(env, A);
+  if ((rc = fill_cfg(cfg, A)) != RLSDE_OK) return rc;
+  if (A.flags & RLSDE_F_STATE_F64) return RLSDE_ERR_UNSUPPORTED;   // the reference differentiates the f32 torch path only
+  if (!(A.flags & RLSDE_F_STORE_PATH)) return RLSDE_ERR_INVALID_ARG;
+  if ((A.flags & RLSDE_F_NOISE_INJECTED) && !noise_dev) return RLSDE_ERR_INVALID_ARG;
+  A.noise = noise_dev;
+  A.G = (void*)G_dev; A.T = (int*)T_dev; A.path = (float*)path_dev;
+  A.counter = (unsigned long long*)workspace_dev;
+  int sm = 0;
+  if ((rc = device_sm_count(&sm)) != RLSDE_OK) return rc;
+  cudaError_t e = cudaMemsetAsync(workspace_dev, 0, WS_COUNTER_BYTES, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+  float* partial = (float*)((char*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES);
+  int lrc = -1;
+#define X(D_, H_) if (env->d == D_ && mlp->d_hidden == H_) lrc = launch_rollout_bwd<D_, H_>(params_host, A, (float)loss_scale, grad_dev, partial, sm, stream);
+  RLSDE_SHAPES(X)
+#undef X
+  if (lrc != 0) return cuda_fail((cudaError_t)lrc, "rollout_bwd launch");
+  return RLSDE_OK;
+}
+
+int rlsde_reduce_stats(int64_t K, int64_t n_steps_lim, uint32_t flags, const void* G_dev, const void* S_dev,
+                       const int32_t* T_dev, const void* l2_dev, const void* logw_dev, double* stats_dev,
+                       void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  if (K < 0 || !G_dev || !S_dev || !T_dev || !stats_dev || !workspace_dev) return RLSDE_ERR_INVALID_ARG;
+  if (workspace_bytes < WS_COUNTER_BYTES + WS_STATS_BYTES) return RLSDE_ERR_WORKSPACE;
+  double* partial = (double*)((char*)workspace_dev + WS_COUNTER_BYTES);
+  const int lrc = launch_reduce_stats(K, n_steps_lim, (flags & RLSDE_F_STATE_F64) != 0, G_dev, S_dev, T_dev, l2_dev, logw_dev,
+                                      stats_dev, partial, (cudaStream_t)stream_);
+  if (lrc != 0) return cuda_fail((cudaError_t)lrc, "reduce_stats launch");
+  return RLSDE_OK;
+}
+
+int rlsde_tables(const double* state_grid_dev, int64_t Ns, const double* action_grid_dev, int64_t Na,
+                 const uint8_t* in_ts_dev, int64_t n_ts, double alpha, double sigma, double dt, double h_half,
+                 double lb, double rb, int64_t sprime_begin, int64_t sprime_end, double* P_dev, double* R_dev,
+                 void* stream_) {
+  if (!state_grid_dev || !action_grid_dev || !in_ts_dev || Ns < 1 || Na < 1 || Ns > 65535) return RLSDE_ERR_INVALID_ARG;
+  if (sprime_begin < 0 || sprime_end > Ns || sprime_begin > sprime_end) return RLSDE_ERR_INVALID_ARG;
+  if (!(dt > 0) || !(sigma > 0) || !(h_half > 0)) return RLSDE_ERR_INVALID_ARG;
+  if (!P_dev && !R_dev) return RLSDE_ERR_INVALID_ARG;
+  const int lrc = launch_tables(state_grid_dev, Ns, action_grid_dev, Na, in_ts_dev, n_ts, alpha, sigma, dt, h_half, lb, rb,
+                                sprime_begin, sprime_end, P_dev, R_dev, (cudaStream_t)stream_);
+  if (lrc != 0) return cuda_fail((cudaError_t)lrc, "tables launch");
+  return RLSDE_OK;
+}
+
+int rlsde_tables_colsum(const double* P_dev, int64_t n_sprime, int64_t Ns, int64_t Na, double* colsum_dev, void* stream_) {
+  if (!P_dev || !colsum_dev || n_sprime < 0 || Ns < 1 || Na < 1) return RLSDE_ERR_INVALID_ARG;
+  const int lrc = launch_tables_colsum(P_dev, n_sprime, Ns, Na, colsum_dev, (cudaStream_t)stream_);
+  if (lrc != 0) return cuda_fail((cudaError_t)lrc, "tables_colsum launch");
+  return RLSDE_OK;
+}
+
+int rlsde_env_step(const rlsde_env* env, int64_t K, const void* state_dev, const float* action_dev,
+                   const float* dbt_in_dev, uint64_t seed, int64_t traj_offset, int64_t pass_index, uint32_t flags,
+                   int32_t reward_type, void* next_state_dev, void* reward_dev, uint8_t* done_dev, float* dbt_out_dev,
+                   void* stream_) {
+  if (!env || env->d < 1 || env->d > RLSDE_MAX_D || K < 0) return RLSDE_ERR_INVALID_ARG;
+  if (!state_dev || !action_dev || !next_state_dev || !reward_dev || !done_dev) return RLSDE_ERR_INVALID_ARG;
+  if (reward_type != RLSDE_REWARD_STATE_ACTION && reward_type != RLSDE_REWARD_STATE_ACTION_NEXT_STATE) return RLSDE_ERR_INVALID_ARG;
+  StepArgs A;
+  memset(&A, 0, sizeof(A));
+  for (int i = 0; i < env->d; ++i) { A.c4a_d[i] = 4.0 * env->alpha[i]; A.c4a_f[i] = (float)(4.0 * env->alpha[i]); }
+  A.sigma_d = env->sigma; A.sigma_f = (float)env->sigma; A.dt_d = env->dt; A.dt_f = (float)env->dt;
+  A.lb_d = env->lb; A.rb_d = env->rb; A.lb_f = (float)env->lb; A.rb_f = (float)env->rb;
+  A.grad_f32 = (flags & RLSDE_F_GRAD_F32) ? 1 : 0;
+  A.noise_scale2 = (float)(-2.0 * env->dt * 0.6931471805599453);
+  A.d = env->d; A.hit_rule = env->hit_rule; A.reward_type = reward_type;
+  A.K = K; A.traj_offset = traj_offset; A.pass_index = pass_index; A.seed = seed;
+  A.state = state_dev; A.action = action_dev; A.dbt_in = dbt_in_dev;
+  A.next_state = next_state_dev; A.reward = reward_dev; A.done = done_dev; A.dbt_out = dbt_out_dev;
+  const int lrc = launch_env_step(A, (flags & RLSDE_F_STATE_F64) != 0, (cudaStream_t)stream_);
+  if (lrc != 0) return cuda_fail((cudaError_t)lrc, "env_step launch");
+  return RLSDE_OK;
+}
+
+int rlsde_noise_fill(uint64_t seed, int64_t traj_offset, int64_t K, int32_t d, int64_t pass_begin, int64_t n_pass,
+                     double dt, float* out_dev, void* stream_) {
+  if (K < 0 || n_pass < 0 || d < 1 || d > RLSDE_MAX_D || !out_dev || !(dt > 0)) return RLSDE_ERR_INVALID_ARG;
+  const int lrc = launch_noise_fill(seed, traj_offset, K, d, pass_begin, n_pass, dt, out_dev, (cudaStream_t)stream_);
+  if (lrc != 0) return cuda_fail((cudaError_t)lrc, "noise_fill launch");
+  return RLSDE_OK;
+}
+
+}  // extern "C"

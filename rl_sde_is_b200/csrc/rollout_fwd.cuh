@@ -1,0 +1,276 @@
+// K1: fused forward rollout (policy MLP + Euler-Maruyama pass + hit bookkeeping + running
+// work / stochastic-integral accumulation), one trajectory per thread, state in registers for
+// the whole rollout, lane refill from a global work counter.
+//
+// Replaces the per-pass Python loops of sample_loss_vectorized (reinforce_deterministic_core.py:52-88),
+// test_policy_vectorized (approximate_methods.py:597-638) and estimate_fht_vectorized (:667-688),
+// i.e. one model.forward + env.step[_torch] (environments.py:139-162,201-226) per pass.
+//
+// Per-pass semantics:
+//   u = policy(X_k);  hit = X_k in target set (CURRENT state);  S += u . dB_{k+1} (also on the hit pass);
+//   hit  -> record (G, S, k) and retire;   else G += -(1 + |u|^2/2) dt;  X_{k+1} = X_k + (-gradV + sigma u) dt + sigma dB.
+// Arithmetic of the pass is written with the reference's association and without FMA contraction
+// so that, given the same action and increment, next state / reward are bit-identical to torch's
+// (f32) or numpy's (f64, RLSDE_F_STATE_F64) results.
+//
+// Scheduling: a warp's 32 lanes run 32 independent trajectories in lock step.  A lane whose
+// trajectory retires takes the next global trajectory id (warp-aggregated atomicAdd) at the next
+// noise-block boundary, so lanes stay busy until the work runs out; the warp leaves the loop when a
+// ballot shows no live lane (first-hitting-time divergence only costs the tail).
+#pragma once
+#include "common.cuh"
+#include "../../include/rlsde.h"
+
+namespace rlsde {
+
+struct FwdArgs {
+  // environment (both precisions are precomputed on the host the way torch / numpy round them)
+  float c4a_f[RLSDE_MAX_D];     // float32(4 * alpha_i)
+  double c4a_d[RLSDE_MAX_D];    // 4 * alpha_i
+  float x0_f[RLSDE_MAX_D];
+  double x0_d[RLSDE_MAX_D];
+  float sigma_f, dt_f, lb_f, rb_f;
+  double sigma_d, dt_d, lb_d, rb_d;
+  float noise_scale2;           // -2 dt ln 2
+  int hit_rule;
+  // work
+  long long K, traj_offset, K_global;
+  unsigned long long seed;
+  long long n_steps_lim, noise_steps;
+  unsigned flags;
+  int ckpt_every;
+  long long ckpt_stride;
+  long long n_grid;
+  double grid_lo, grid_hi, grid_h;
+  // buffers
+  const float* noise;
+  const float* policy_opt;
+  void* G;
+  void* S;
+  int* T;
+  void* l2;
+  void* logw;
+  float* path;
+  unsigned long long* counter;
+};
+
+template <bool F64> struct RealT { typedef float type; };
+template <> struct RealT<true> { typedef double type; };
+
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+template <int D>
+struct NoisePlan {
+  // passes served by one Philox block (D = 1, 2) or blocks needed per pass (D >= 3)
+  static constexpr int SPB = (D == 1) ? 4 : (D == 2 ? 2 : 1);
+  static constexpr int BPP = (D <= 2) ? 1 : (D + 3) / 4;
+  static constexpr int NZ = 4 * BPP;
+};
+
+template <int D, int H, bool F64, bool FAST>
+__global__ void __launch_bounds__(128) rollout_fwd_kernel(const __grid_constant__ MlpConst<D, H> W,
+                                                          const __grid_constant__ FwdArgs A) {
+  typedef typename RealT<F64>::type real;
+  constexpr int SPB = NoisePlan<D>::SPB;
+  constexpr int BPP = NoisePlan<D>::BPP;
+  constexpr int NZ = NoisePlan<D>::NZ;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const bool inject = (A.flags & RLSDE_F_NOISE_INJECTED) != 0;
+  const bool s_exact = (A.flags & RLSDE_F_STOCH_INT_EXACT) != 0;
+  const bool store_path = (A.flags & RLSDE_F_STORE_PATH) != 0 && A.path != nullptr;
+  const bool want_l2 = (D == 1) && A.policy_opt != nullptr && A.l2 != nullptr;
+  const long long lim = inject ? (A.noise_steps < A.n_steps_lim ? A.noise_steps : A.n_steps_lim) : A.n_steps_lim;
+
+  bool alive = false, exhausted = false;
+  long long traj = 0;
+  int k = 0, ck = 0;
+  real x[D];
+  real G = 0, S = 0, L2 = 0;
+  float z[NZ];
+#pragma unroll
+  for (int i = 0; i < D; ++i) x[i] = F64 ? (real)A.x0_d[i] : (real)A.x0_f[i];
+#pragma unroll
+  for (int i = 0; i < NZ; ++i) z[i] = 0.f;
+
+  for (unsigned it = 0;; ++it) {
+    if ((it & (SPB - 1)) == 0) {
+      const unsigned need = __ballot_sync(FULL, !alive && !exhausted);
+      if (need) {
+        unsigned long long base = 0;
+        const int leader = __ffs(need) - 1;
+        if (lane == leader) base = atomicAdd(A.counter, (unsigned long long)__popc(need));
+        base = __shfl_sync(FULL, base, leader);
+        if (!alive && !exhausted) {
+          const long long idx = (long long)base + __popc(need & ((1u << lane) - 1u));
+          if (idx < A.K) {
+            traj = idx; k = 0; ck = 0; alive = true;
+            G = 0; S = 0; L2 = 0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) x[i] = F64 ? (real)A.x0_d[i] : (real)A.x0_f[i];
+          } else {
+            exhausted = true;
+          }
+        }
+      }
+      if (!__any_sync(FULL, alive)) break;
+      if (!inject) {
+        const unsigned long long gt = (unsigned long long)(A.traj_offset + traj);
+#pragma unroll
+        for (int q = 0; q < BPP; ++q) {
+          float zz[4];
+          noise_block(A.seed, gt, (unsigned)(k / SPB) * BPP + q, A.noise_scale2, zz);
+#pragma unroll
+          for (int s = 0; s < 4; ++s) z[4 * q + s] = zz[s];
+        }
+      }
+    }
+
+    // ---- policy
+    float xf[D], u[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) xf[i] = (float)x[i];
+    mlp_forward<D, H, FAST>(W, xf, u);
+
+    // ---- this pass's Brownian increments
+    float dB[D];
+    if (inject) {
+      const long long row = (long long)k * A.K_global + (A.traj_offset + traj);
+#pragma unroll
+      for (int i = 0; i < D; ++i) dB[i] = (alive && k < lim) ? __ldg(A.noise + row * D + i) : 0.f;
+    } else {
+      const int sub = (int)(it & (SPB - 1));
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        if constexpr (SPB == 1) {
+          dB[i] = z[i];
+        } else {
+          float v = z[i];
+#pragma unroll
+          for (int s = 1; s < SPB; ++s) v = (sub == s) ? z[s * D + i] : v;
+          dB[i] = v;
+        }
+      }
+    }
+
+    // ---- hit test on the current state
+    bool hit;
+    if (A.hit_rule == RLSDE_HIT_X0_IN_LB_RB) {
+      hit = F64 ? ((double)x[0] >= A.lb_d && (double)x[0] <= A.rb_d) : ((float)x[0] >= A.lb_f && (float)x[0] <= A.rb_f);
+    } else {
+      hit = true;
+#pragma unroll
+      for (int i = 0; i < D; ++i) hit = hit && (F64 ? ((double)x[i] >= A.lb_d) : ((float)x[i] >= A.lb_f));
+    }
+
+    // ---- stochastic integral, running cost, l2 error
+    real su = 0;
+    float n2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      su = (i == 0) ? mul_rn((real)u[i], (real)dB[i]) : add_rn(su, mul_rn((real)u[i], (real)dB[i]));
+      n2 = (i == 0) ? __fmul_rn(u[i], u[i]) : __fadd_rn(n2, __fmul_rn(u[i], u[i]));
+    }
+    const real S_prev = S;
+    S = add_rn(S, su);
+    if (want_l2) {
+      // idx = floor((clip(x) - lo) / h)   environments.py:318-321;  |u - u_opt|^2 dt  approximate_methods.py:610-615
+      double xc = (double)x[0];
+      xc = xc < A.grid_lo ? A.grid_lo : (xc > A.grid_hi ? A.grid_hi : xc);
+      long long gi = (long long)floor((xc - A.grid_lo) / A.grid_h);
+      gi = gi < 0 ? 0 : (gi >= A.n_grid ? A.n_grid - 1 : gi);
+      const float uo = alive ? __ldg(A.policy_opt + gi) : 0.f;
+      const float du = __fsub_rn(u[0], uo);
+      L2 = F64 ? (real)__dadd_rn((double)L2, __dmul_rn((double)__fmul_rn(du, du), A.dt_d))
+               : (real)__fadd_rn((float)L2, __fmul_rn(__fmul_rn(du, du), A.dt_f));
+    }
+
+    if (alive) {
+      if (store_path) {
+        if (ck == 0) {
+          float* dst = A.path + ((long long)traj * A.ckpt_stride + k / A.ckpt_every) * D;
+#pragma unroll
+          for (int i = 0; i < D; ++i) dst[i] = (float)x[i];
+          ck = A.ckpt_every;
+        }
+        --ck;
+      }
+      if (hit) {
+        const real Sout = s_exact ? S_prev : S;
+        if (F64) {
+          ((double*)A.G)[traj] = (double)G;
+          ((double*)A.S)[traj] = (double)Sout;
+          if (A.l2) ((double*)A.l2)[traj] = (double)L2;
+          if (A.logw) ((double*)A.logw)[traj] = (double)G - (double)S_prev;
+        } else {
+          ((float*)A.G)[traj] = (float)G;
+          ((float*)A.S)[traj] = (float)Sout;
+          if (A.l2) ((float*)A.l2)[traj] = (float)L2;
+          if (A.logw) ((float*)A.logw)[traj] = (float)G - (float)S_prev;
+        }
+        A.T[traj] = k;
+        alive = false;
+      } else {
+        // running cost  r = -(1 + 0.5 |u|^2) dt   (environments.py:104-110,121-127; f = 1, g = 0)
+        if (F64) {
+          // numpy: f (float64 ones) + float32(0.5 * norm(a)^2)  -> float64, times python-float dt
+          const float nn = (D == 1) ? n2 : __fmul_rn(sqrtf(n2), sqrtf(n2));
+          const double r = -__dmul_rn(__dadd_rn(1.0, (double)__fmul_rn(0.5f, nn)), A.dt_d);
+          G = (real)__dadd_rn((double)G, r);
+        } else {
+          const float nn = (D == 1) ? n2 : __fmul_rn(sqrtf(n2), sqrtf(n2));
+          const float r = -__fmul_rn(__fadd_rn(1.0f, __fmul_rn(0.5f, nn)), A.dt_f);
+          G = (real)__fadd_rn((float)G, r);
+        }
+        // Euler-Maruyama:  x + (-gradV(x) + sigma u) dt + sigma dB,  gradV = 4 alpha x (x^2 - 1)
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          if (F64) {
+            const double xi = (double)x[i];
+            double g;
+            if (D == 1 && k == 0) {
+              // numpy 1-D: the first pass sees a float32 state and a python-float alpha -> float32 gradient
+              const float xs = (float)xi;
+              g = (double)__fmul_rn(__fmul_rn(A.c4a_f[i], xs), __fsub_rn(__fmul_rn(xs, xs), 1.0f));
+            } else {
+              g = __dmul_rn(__dmul_rn(A.c4a_d[i], xi), __dsub_rn(__dmul_rn(xi, xi), 1.0));
+            }
+            const double drift = __dmul_rn(__dadd_rn(-g, __dmul_rn(A.sigma_d, (double)u[i])), A.dt_d);
+            x[i] = (real)__dadd_rn(__dadd_rn(xi, drift), __dmul_rn(A.sigma_d, (double)dB[i]));
+          } else {
+            const float xi = (float)x[i];
+            const float g = __fmul_rn(__fmul_rn(A.c4a_f[i], xi), __fsub_rn(__fmul_rn(xi, xi), 1.0f));
+            const float drift = __fmul_rn(__fadd_rn(-g, __fmul_rn(A.sigma_f, u[i])), A.dt_f);
+            x[i] = (real)__fadd_rn(__fadd_rn(xi, drift), __fmul_rn(A.sigma_f, dB[i]));
+          }
+        }
+        ++k;
+        if (k >= lim) {
+          // not detected within the pass budget: flagged, never garbage (failure row)
+          if (F64) {
+            ((double*)A.G)[traj] = (double)G;
+            ((double*)A.S)[traj] = (double)S;
+            if (A.l2) ((double*)A.l2)[traj] = (double)L2;
+            if (A.logw) ((double*)A.logw)[traj] = (double)G - (double)S;
+          } else {
+            ((float*)A.G)[traj] = (float)G;
+            ((float*)A.S)[traj] = (float)S;
+            if (A.l2) ((float*)A.l2)[traj] = (float)L2;
+            if (A.logw) ((float*)A.logw)[traj] = (float)G - (float)S;
+          }
+          A.T[traj] = -1;
+          alive = false;
+        }
+      }
+    }
+  }
+}
+
+// host-side launcher for one (D, H) shape; defined in rollout_fwd_inst.cuh
+template <int D, int H>
+int launch_rollout_fwd(const float* params_host, const FwdArgs& args, int sm_count, cudaStream_t stream);
+
+}  // namespace rlsde

@@ -1,0 +1,46 @@
+// Launcher + explicit instantiation helper for one policy shape (D, H) of the forward rollout.
+#pragma once
+#include "rollout_fwd.cuh"
+
+namespace rlsde {
+
+template <int D, int H, bool F64, bool FAST>
+static int launch_fwd_variant(const float* params_host, const FwdArgs& args, int sm_count, cudaStream_t stream) {
+  MlpConst<D, H> W;
+  pack_mlp_const<D, H>(params_host, FAST, W);
+  auto kern = rollout_fwd_kernel<D, H, F64, FAST>;
+  // Small batches: one warp per block so the warps spread over SMs (latency-bound regime);
+  // large batches: persistent grid of 128-thread blocks, as many as are co-resident.
+  int block = 128;
+  long long grid;
+  if (args.K <= (long long)sm_count * 128) {
+    block = 32;
+    grid = (args.K + 31) / 32;
+  } else {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    grid = (long long)sm_count * per_sm;
+    const long long need = (args.K + block - 1) / block;
+    if (grid > need) grid = need;
+  }
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, block, 0, stream>>>(W, args);
+  return (int)cudaGetLastError();
+}
+
+template <int D, int H>
+int launch_rollout_fwd(const float* params_host, const FwdArgs& args, int sm_count, cudaStream_t stream) {
+  const bool f64 = (args.flags & RLSDE_F_STATE_F64) != 0;
+  const bool fast = (args.flags & RLSDE_F_TANH_FAST) != 0;
+  if (f64) {
+    return fast ? launch_fwd_variant<D, H, true, true>(params_host, args, sm_count, stream)
+                : launch_fwd_variant<D, H, true, false>(params_host, args, sm_count, stream);
+  }
+  return fast ? launch_fwd_variant<D, H, false, true>(params_host, args, sm_count, stream)
+              : launch_fwd_variant<D, H, false, false>(params_host, args, sm_count, stream);
+}
+
+}  // namespace rlsde
+
+#define RLSDE_INSTANTIATE_FWD(D, H) \
+  template int rlsde::launch_rollout_fwd<D, H>(const float*, const rlsde::FwdArgs&, int, cudaStream_t);

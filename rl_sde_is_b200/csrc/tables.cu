@@ -1,0 +1,117 @@
+// K4: tabular transition tensor P[s', s, a] and reward table R[s, a]  (float64).
+//
+// Replaces compute_p_tensor_batch / compute_r_table (dynamic_programming.py:3-36), i.e. 180 300
+// Python iterations x 4 scipy.stats.norm.cdf calls at h = 0.01, and the per-column arithmetic of
+// state_action_transition_function (environments.py:87-102):
+//     mu = x_s + (-gradV(x_s) + sigma a) dt,  sd = sigma sqrt(dt)
+//     P[s', s, a] = Phi((x_s' + h - mu) / sd) - Phi((x_s' - h - mu) / sd)       s outside the target set
+//     P[0,   s, a] += Phi((x_0 - h - mu) / sd);   P[N-1, s, a] += 1 - Phi((x_{N-1} + h - mu) / sd)
+//     P[s', s, a] = 1/|TS| if s' in TS else 0                                     s in the target set
+//
+// Layout / mapping: the tensor is C-ordered with the action index innermost, so a warp's 32 lanes
+// take 32 consecutive actions (each store instruction writes 256 contiguous bytes) and every thread
+// walks TILE consecutive next-states, carrying the CDF of the shared cell edge from one cell to the
+// next (TILE+1 CDF evaluations per TILE entries instead of 2 TILE).  The kernel is bound by the FP64
+// pipe (erf/erfc), not by HBM: see DESIGN.md.
+#include "aux_kernels.cuh"
+
+namespace rlsde {
+
+// scipy.special.ndtr (cephes ndtr.c) branch structure, with CUDA's erf / erfc
+__device__ __forceinline__ double ndtr(double a) {
+  const double kSqrtH = 0.70710678118654752440;
+  const double x = a * kSqrtH;
+  const double z = fabs(x);
+  double y;
+  if (z < kSqrtH) {
+    y = 0.5 + 0.5 * erf(x);
+  } else {
+    y = 0.5 * erfc(z);
+    if (x > 0) y = 1.0 - y;
+  }
+  return y;
+}
+
+constexpr int TABLE_TILE = 8;
+
+__global__ void __launch_bounds__(128) tables_kernel(const double* __restrict__ sgrid, long long Ns,
+                                                     const double* __restrict__ agrid, long long Na,
+                                                     const unsigned char* __restrict__ in_ts, double inv_nts,
+                                                     double alpha, double sigma, double dt, double h,
+                                                     long long sp_begin, long long sp_end, double* __restrict__ P) {
+  const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long s = blockIdx.y;
+  const long long sp0 = sp_begin + (long long)blockIdx.z * TABLE_TILE;
+  if (a >= Na || sp0 >= sp_end) return;
+  const long long sp1 = sp0 + TABLE_TILE < sp_end ? sp0 + TABLE_TILE : sp_end;
+  double* out = P + ((sp0 - sp_begin) * Ns + s) * Na + a;
+  const long long stride = Ns * Na;
+  if (in_ts[s]) {
+    for (long long sp = sp0; sp < sp1; ++sp, out += stride) *out = in_ts[sp] ? inv_nts : 0.0;
+    return;
+  }
+  const double xs = sgrid[s];
+  const double act = agrid[a];
+  // mu = state + (-gradient(state) + sigma * action) * dt,  gradient = 4 alpha x (x^2 - 1)
+  const double grad = __dmul_rn(__dmul_rn(__dmul_rn(4.0, alpha), xs), __dsub_rn(__dmul_rn(xs, xs), 1.0));
+  const double mu = __dadd_rn(xs, __dmul_rn(__dadd_rn(-grad, __dmul_rn(sigma, act)), dt));
+  const double sd = __dmul_rn(sigma, sqrt(dt));
+  double lo = ndtr(__ddiv_rn(__dsub_rn(__dsub_rn(sgrid[sp0], h), mu), sd));
+  for (long long sp = sp0; sp < sp1; ++sp, out += stride) {
+    // upper edge of cell sp = lower edge of cell sp+1 (x_{sp+1} - h); the last cell of the tile /
+    // of the grid uses its own x_sp + h
+    const double edge = (sp + 1 < sp1) ? __dsub_rn(sgrid[sp + 1], h) : __dadd_rn(sgrid[sp], h);
+    const double hi = ndtr(__ddiv_rn(__dsub_rn(edge, mu), sd));
+    double p = hi - lo;
+    if (sp == 0) p += lo;                 // left tail folded into the first row
+    if (sp == Ns - 1) p += 1.0 - hi;      // right tail folded into the last row
+    *out = p;
+    lo = hi;
+  }
+}
+
+__global__ void rtable_kernel(long long Ns, const double* __restrict__ agrid, long long Na,
+                              const unsigned char* __restrict__ in_ts, double dt, double* __restrict__ R) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= Ns * Na) return;
+  const long long s = e / Na, a = e % Na;
+  const double act = agrid[a];
+  // where(done, -g(x) = -0.0, -(f + 0.5 |a|^2) dt)   environments.py:104-110
+  R[e] = in_ts[s] ? -0.0 : -__dmul_rn(__dadd_rn(1.0, __dmul_rn(0.5, __dmul_rn(act, act))), dt);
+}
+
+int launch_tables(const double* state_grid, long long Ns, const double* action_grid, long long Na,
+                  const unsigned char* in_ts, long long n_ts, double alpha, double sigma, double dt, double h_half,
+                  double lb, double rb, long long sprime_begin, long long sprime_end, double* P, double* R,
+                  cudaStream_t stream) {
+  (void)lb; (void)rb;
+  if (P && sprime_end > sprime_begin) {
+    const long long nsp = sprime_end - sprime_begin;
+    dim3 grid((unsigned)((Na + 127) / 128), (unsigned)Ns, (unsigned)((nsp + TABLE_TILE - 1) / TABLE_TILE));
+    tables_kernel<<<grid, 128, 0, stream>>>(state_grid, Ns, action_grid, Na, in_ts, n_ts > 0 ? 1.0 / (double)n_ts : 0.0,
+                                            alpha, sigma, dt, h_half, sprime_begin, sprime_end, P);
+  }
+  if (R) {
+    const long long n = Ns * Na;
+    rtable_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(Ns, action_grid, Na, in_ts, dt, R);
+  }
+  return (int)cudaGetLastError();
+}
+
+// colsum[s, a] += sum over the slab's next-states, in index order (deterministic)
+__global__ void colsum_kernel(const double* __restrict__ P, long long n_sprime, long long cols, double* __restrict__ colsum) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double a = colsum[c];
+  for (long long sp = 0; sp < n_sprime; ++sp) a += P[sp * cols + c];
+  colsum[c] = a;
+}
+
+int launch_tables_colsum(const double* P, long long n_sprime, long long Ns, long long Na, double* colsum,
+                         cudaStream_t stream) {
+  const long long cols = Ns * Na;
+  colsum_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, stream>>>(P, n_sprime, cols, colsum);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace rlsde

@@ -1,0 +1,169 @@
+"""Deterministic-policy REINFORCE on the fused rollout kernels (drop-in for the reference module).
+
+Reference: rl_sde_is/reinforce_deterministic_core.py
+  * ``sample_loss_vectorized(env, model, K)`` (:30-93)  -> one K1 launch (+ K2 when ``.backward()`` runs)
+  * ``reinforce(env, ...)`` (:102-336)                  -> same arguments, same keys in the returned dict
+
+Keyword-only extras (defaults = reference behaviour): ``noise`` (injected increments
+``[n_steps, K, d]``), ``seed`` (Philox key), ``n_steps_lim``, ``tanh`` ('precise' | 'fast'),
+``stoch_int`` ('reference' | 'exact'), ``ckpt_every``, ``device``, ``dist`` (shard the batch over a
+torch.distributed process group and all-reduce the packed gradient + statistics).
+"""
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.optim as optim
+
+from . import _lib as L
+from . import rollout as R
+from .models import DeterministicPolicy, mlp  # noqa: F401  (re-exported like the reference module)
+
+_call_counter = [0]
+
+
+def _next_seed(seed):
+    """Rollouts without an explicit seed draw a fresh Philox key from torch's CPU generator, so that
+    ``torch.manual_seed(s)`` makes a run reproducible the way it does for the reference."""
+    if seed is not None:
+        return int(seed)
+    return int(torch.randint(0, 2**62, (1,), dtype=torch.int64).item())
+
+
+def sample_loss_vectorized(env, model, K, *, noise=None, seed=None, n_steps_lim=10**6, tanh="precise",
+                           stoch_int="reference", ckpt_every=None, device=None, dist=None):
+    """Sample K trajectories under the policy and return ``(eff_loss, return_fht, time_steps)``.
+
+    ``eff_loss`` is a 0-d float32 tensor (on the parameters' device) whose ``.backward()`` fills
+    ``p.grad`` of ``model.parameters()``; ``return_fht`` is ``np.float32[K]`` and ``time_steps``
+    ``np.float64[K]`` (= k*+1, the 1-based pass on which the hit is detected), as in the reference.
+    With ``dist`` the K trajectories are this rank's shard of ``dist.K_global``; the loss is the global
+    mean and the gradient is all-reduced inside ``backward``.
+    """
+    d, H = R.policy_shape(model)
+    if d != env.d:
+        raise L.RlsdeError(f"policy dimension {d} != env.d {env.d}")
+    env_c = R.env_struct(env, L.HIT_ALL_GE_LB)          # torch path: x >= lb only (environments.py:51-52)
+    mlp_c = L.make_mlp(d, H)
+    dev = R._cuda_device(device)
+    if noise is not None and not torch.is_tensor(noise):
+        noise = torch.as_tensor(np.ascontiguousarray(noise, dtype=np.float32))
+    if noise is not None:
+        noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+    lim = int(n_steps_lim) if noise is None else min(int(n_steps_lim), int(noise.shape[0]))
+    if ckpt_every is None:
+        ckpt_every = R.choose_ckpt_every(int(K), d, lim)
+    opts = dict(seed=_next_seed(seed), n_steps_lim=n_steps_lim, noise=noise, tanh=tanh, stoch_int=stoch_int,
+                ckpt_every=ckpt_every, device=dev)
+    if dist is not None:
+        opts.update(traj_offset=dist.traj_offset, K_global=dist.K_global)
+    flat = R.flat_parameters(model)
+    holder = {}
+    loss = _LossWithAux.apply(flat, env_c, mlp_c, int(K), opts, holder, dist)
+    out = holder["out"]
+    T = out.T.cpu().numpy()
+    if (T < 0).any():
+        # the reference would hand back uninitialised torch.empty values here (:41-43); we refuse instead
+        raise L.RlsdeError(f"{int((T < 0).sum())} of {K} trajectories did not reach the target set within "
+                           f"{lim} passes; raise n_steps_lim")
+    return loss, out.G.cpu().numpy(), (T + 1).astype(np.float64)
+
+
+class _LossWithAux(torch.autograd.Function):
+    """RolloutLoss that also hands the raw rollout back to the caller (and reduces across ranks)."""
+
+    @staticmethod
+    def forward(ctx, flat_params, env_c, mlp_c, K, opts, holder, dist):
+        params_host = flat_params.detach().to("cpu", torch.float32).contiguous().numpy()
+        out = R.rollout_forward(env_c, mlp_c, params_host, K, store_path=True, want_logw=False, **opts)
+        holder["out"] = out
+        K_global = out.cfg.K_global
+        if dist is not None:
+            stats = dist.all_reduce_sum(out.stats_dev.clone())
+            loss = float(stats[L.ST_SUM_LOSS].item()) / K_global
+            holder["stats_global"] = stats.cpu().numpy()
+        else:
+            loss = out.stats[L.ST_SUM_LOSS] / K_global
+        ctx.env_c, ctx.mlp_c, ctx.params_host, ctx.out, ctx.opts, ctx.dist = env_c, mlp_c, params_host, out, opts, dist
+        return torch.tensor(loss, dtype=torch.float32, device=flat_params.device)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        out = ctx.out
+        g = R.rollout_backward(ctx.env_c, ctx.mlp_c, ctx.params_host, out, 1.0 / out.cfg.K_global,
+                               noise=ctx.opts.get("noise"), device=ctx.opts.get("device"))
+        if ctx.dist is not None:
+            g = ctx.dist.all_reduce_sum(g)
+        g = g.to(grad_out.device) * grad_out.to(torch.float32)
+        return g, None, None, None, None, None, None
+
+
+def reinforce(env, gamma=1., d_hidden_layer=256, n_layers=3, batch_size=1000, lr=1e-3, n_iterations=100, seed=None,
+              test_batch_size=1000, test_freq_iterations=100, backup_freq_iterations=None, policy_opt=None,
+              load=False, test=False, live_plot=False, *, save_fn=None, verbose=True, **rollout_opts):
+    """Training loop with the reference's signature and result dictionary (:102-336).
+
+    Differences that do not change results: plotting (``live_plot``) and the on-disk layout
+    (``load`` / backups through rl_sde_is.utils_path) are out of the hot path's scope; ``save_fn(data,
+    model, iteration)`` is called where the reference writes a backup.  ``gamma`` is accepted and unused,
+    as in the reference (:108-117).
+    """
+    if load:
+        raise NotImplementedError("loading reference run directories is outside the hot-path scope (SURVEY 8f-2)")
+    from .approximate_methods import test_policy_vectorized
+
+    if seed is not None:
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+    hidden = [d_hidden_layer] * (n_layers - 1)
+    model = DeterministicPolicy(state_dim=env.state_space_dim, action_dim=env.action_space_dim,
+                                hidden_sizes=hidden, activation=nn.Tanh())
+    optimizer = optim.Adam(model.parameters(), lr=lr)
+    data = dict(gamma=gamma, n_layers=n_layers, d_hidden_layer=d_hidden_layer, batch_size=batch_size, lr=lr,
+                n_iterations=n_iterations, seed=seed, backup_freq_iterations=backup_freq_iterations, model=model)
+    returns = np.empty(0, dtype=np.float32)
+    time_steps = np.empty(0, dtype=np.int32)
+    losses, exp_returns, var_returns, exp_time_steps, cts = (np.full(n_iterations, np.nan) for _ in range(5))
+    tests = {k: np.empty(0, dtype=np.float32) for k in ("mean_returns", "var_returns", "mean_lengths", "policy_l2_errors")}
+
+    def run_test(it):
+        res = test_policy_vectorized(env, model, batch_size=test_batch_size, policy_opt=policy_opt)
+        for key, val in zip(tests, res):
+            tests[key] = np.append(tests[key], val)
+        if verbose:
+            print("it.: {:3d}, test mean return: {:2.2f}, test var return: {:.2e}, test mean time steps: {:2.2f}".format(
+                it, res[0], res[1], res[2]))
+
+    if test:
+        data.update(test_freq_iterations=test_freq_iterations, test_batch_size=test_batch_size)
+        run_test(0)
+
+    for i in range(n_iterations):
+        t0 = time.time()
+        optimizer.zero_grad()
+        eff_loss, batch_returns, batch_time_steps = sample_loss_vectorized(env, model, batch_size, **rollout_opts)
+        eff_loss.backward()
+        optimizer.step()
+        cts[i] = time.time() - t0          # wall clock of zero_grad -> loss -> backward -> step, like the reference's ct
+
+        returns = np.append(returns, batch_returns)
+        time_steps = np.append(time_steps, batch_time_steps)
+        losses[i] = float(eff_loss.detach())
+        exp_returns[i] = np.mean(batch_returns)
+        var_returns[i] = np.var(batch_returns)
+        exp_time_steps[i] = np.mean(batch_time_steps)
+        if verbose:
+            print("it.: {:2d}, loss: {:.3e}, exp return: {:.3e}, var return: {:.1e}, ct: {:.3f}".format(
+                i, losses[i], exp_returns[i], var_returns[i], cts[i]))
+        if test and (i + 1) % test_freq_iterations == 0:
+            run_test(i + 1)
+        if backup_freq_iterations is not None and (i + 1) % backup_freq_iterations == 0 and save_fn is not None:
+            save_fn(data, model, i + 1)
+
+    data.update(returns=returns, time_steps=time_steps, losses=losses, exp_returns=exp_returns,
+                var_returns=var_returns, exp_time_steps=exp_time_steps, cts=cts)
+    if test:
+        data.update(test_mean_returns=tests["mean_returns"], test_var_returns=tests["var_returns"],
+                    test_mean_lengths=tests["mean_lengths"], test_policy_l2_errors=tests["policy_l2_errors"])
+    return data

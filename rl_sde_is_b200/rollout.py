@@ -1,0 +1,248 @@
+"""Device-side rollout API: thin, typed wrappers over the C ABI plus the autograd Function.
+
+This is the layer the reference-named drop-ins (reinforce_deterministic_core.sample_loss_vectorized,
+approximate_methods.test_policy_vectorized, ...) are built on.  Tensors are torch CUDA tensors used
+only as device memory; all arithmetic happens in librlsde_b200.so.
+"""
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+# ---------------------------------------------------------------------------------------------------
+# env / policy description
+# ---------------------------------------------------------------------------------------------------
+def env_struct(env, hit_rule):
+    """rlsde_env from any object with the reference env's attributes (environments.py:7-40)."""
+    d = int(env.d)
+    x0 = np.asarray(env.state_init, dtype=np.float64).reshape(-1)
+    return L.make_env(d, env.alpha, float(env.sigma), float(env.dt), float(env.lb), float(env.rb), x0, hit_rule)
+
+
+def policy_linears(model):
+    """The nn.Linear layers of a reference-style policy (models.py:4-18 + DeterministicPolicy)."""
+    seq = getattr(model, "policy", model)
+    linears = [m for m in seq.modules() if isinstance(m, torch.nn.Linear)]
+    acts = [m for m in seq.modules() if isinstance(m, (torch.nn.Tanh, torch.nn.ReLU, torch.nn.Sigmoid, torch.nn.ELU))]
+    if len(linears) != 3:
+        raise L.RlsdeError(f"fused kernels cover 2 hidden layers (n_layers=3, what the reference builds); got {len(linears)} Linear layers")
+    if not all(isinstance(a, torch.nn.Tanh) for a in acts):
+        raise L.RlsdeError("fused kernels cover Tanh hidden activations (what the reference uses)")
+    return linears
+
+
+def policy_shape(model):
+    l1, l2, l3 = policy_linears(model)
+    d, H = l1.in_features, l1.out_features
+    if l2.in_features != H or l2.out_features != H or l3.in_features != H or l3.out_features != d:
+        raise L.RlsdeError("policy must be d -> H -> H -> d")
+    return d, H
+
+
+def flat_parameters(model):
+    """Differentiable flat view of the policy parameters in state_dict order."""
+    ps = []
+    for lin in policy_linears(model):
+        ps += [lin.weight.reshape(-1), lin.bias.reshape(-1)]
+    return torch.cat(ps)
+
+
+_workspaces = {}
+
+
+def _workspace(device):
+    key = (device.type, device.index)
+    ws = _workspaces.get(key)
+    if ws is None:
+        n = L.load().rlsde_workspace_bytes(0)
+        ws = torch.empty(n, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _cuda_device(device=None):
+    if not torch.cuda.is_available():
+        raise L.RlsdeError("a CUDA device is required (no CPU fallback)")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise L.RlsdeError("device must be a CUDA device")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+@dataclass
+class RolloutOut:
+    G: torch.Tensor                     # return_fht, float32 (float64 with state_f64)
+    S: torch.Tensor                     # stoch_int_fht
+    T: torch.Tensor                     # int32 hit index k* (-1 = not detected within n_steps_lim)
+    l2: Optional[torch.Tensor]
+    logw: Optional[torch.Tensor]
+    path: Optional[torch.Tensor]
+    stats_dev: torch.Tensor             # float64[RLSDE_NSTATS] on the device
+    cfg: object = None
+    _stats: Optional[np.ndarray] = None
+
+    @property
+    def stats(self):
+        """Host copy of the statistics record (synchronises on first access)."""
+        if self._stats is None:
+            self._stats = self.stats_dev.cpu().numpy()
+        return self._stats
+
+
+def rollout_forward(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=10**6, noise=None, traj_offset=0,
+                    K_global=None, tanh="precise", stoch_int="reference", state_f64=False, store_path=False,
+                    ckpt_every=1, policy_opt=None, grid=None, want_logw=True, device=None, out=None):
+    """One launch of K1 for K trajectories.  ``params_host``: contiguous float32 numpy array (state_dict order)."""
+    lib = L.load()
+    dev = _cuda_device(device)
+    K = int(K)
+    d = env_c.d
+    params_host = np.ascontiguousarray(params_host, dtype=np.float32)
+    if params_host.size != lib.rlsde_param_count(mlp_c):
+        raise L.RlsdeError(f"expected {lib.rlsde_param_count(mlp_c)} policy parameters, got {params_host.size}")
+    flags = 0
+    cfg = L.RlsdeRolloutCfg()
+    cfg.K, cfg.traj_offset, cfg.K_global = K, int(traj_offset), int(K_global if K_global is not None else K)
+    cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    cfg.n_steps_lim = int(n_steps_lim)
+    if noise is not None:
+        if noise.device != dev or noise.dtype != torch.float32 or not noise.is_contiguous():
+            raise L.RlsdeError("noise must be a contiguous float32 CUDA tensor [n_steps, K_global, d]")
+        if noise.dim() != 3 or noise.shape[1] != cfg.K_global or noise.shape[2] != d:
+            raise L.RlsdeError(f"noise must have shape [n_steps, {cfg.K_global}, {d}], got {tuple(noise.shape)}")
+        flags |= L.F_NOISE_INJECTED
+        cfg.noise_steps = int(noise.shape[0])
+    if tanh == "fast":
+        flags |= L.F_TANH_FAST
+    elif tanh != "precise":
+        raise L.RlsdeError("tanh must be 'precise' or 'fast'")
+    if stoch_int == "exact":
+        flags |= L.F_STOCH_INT_EXACT
+    elif stoch_int != "reference":
+        raise L.RlsdeError("stoch_int must be 'reference' or 'exact'")
+    real = torch.float64 if state_f64 else torch.float32
+    if state_f64:
+        flags |= L.F_STATE_F64
+    path = None
+    if store_path:
+        flags |= L.F_STORE_PATH
+        lim_eff = min(cfg.n_steps_lim, cfg.noise_steps) if noise is not None else cfg.n_steps_lim
+        cfg.ckpt_every = int(ckpt_every)
+        cfg.ckpt_stride = (lim_eff + cfg.ckpt_every - 1) // cfg.ckpt_every
+        path = torch.empty((K, cfg.ckpt_stride, d), dtype=torch.float32, device=dev)
+    pol = None
+    if policy_opt is not None:
+        pol = torch.as_tensor(np.ascontiguousarray(np.asarray(policy_opt, dtype=np.float32).reshape(-1)), device=dev) \
+            if not torch.is_tensor(policy_opt) else policy_opt.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        lo, hi, h = grid
+        cfg.n_grid, cfg.grid_lo, cfg.grid_hi, cfg.grid_h = int(pol.numel()), float(lo), float(hi), float(h)
+    cfg.flags = flags
+    G = torch.empty(K, dtype=real, device=dev)
+    S = torch.empty(K, dtype=real, device=dev)
+    T = torch.empty(K, dtype=torch.int32, device=dev)
+    l2 = torch.empty(K, dtype=real, device=dev) if pol is not None else None
+    logw = torch.empty(K, dtype=real, device=dev) if want_logw else None
+    stats = torch.zeros(L.RLSDE_NSTATS, dtype=torch.float64, device=dev)
+    ws = _workspace(dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.rlsde_rollout_fwd(env_c, mlp_c, params_host.ctypes.data, cfg, _ptr(noise), _ptr(pol), _ptr(G), _ptr(S),
+                                   _ptr(T), _ptr(l2), _ptr(logw), _ptr(path), _ptr(stats), _ptr(ws), ws.numel(), stream)
+    L.check(rc, "rlsde_rollout_fwd")
+    return RolloutOut(G=G, S=S, T=T, l2=l2, logw=logw, path=path, stats_dev=stats, cfg=cfg)
+
+
+def rollout_backward(env_c, mlp_c, params_host, fwd: RolloutOut, loss_scale, *, noise=None, device=None):
+    """K2: gradient of loss_scale * sum_k(-G_k - sg(G_k) S_k) w.r.t. the flat parameters (float32 CUDA tensor)."""
+    lib = L.load()
+    dev = _cuda_device(device)
+    if fwd.path is None:
+        raise L.RlsdeError("the forward rollout must be run with store_path=True")
+    params_host = np.ascontiguousarray(params_host, dtype=np.float32)
+    grad = torch.empty(int(lib.rlsde_param_count(mlp_c)), dtype=torch.float32, device=dev)
+    ws = _workspace(dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.rlsde_rollout_bwd(env_c, mlp_c, params_host.ctypes.data, fwd.cfg, _ptr(noise), _ptr(fwd.G), _ptr(fwd.T),
+                                   _ptr(fwd.path), float(loss_scale), _ptr(grad), _ptr(ws), ws.numel(), stream)
+    L.check(rc, "rlsde_rollout_bwd")
+    return grad
+
+
+def choose_ckpt_every(K, d, n_steps_lim, budget_bytes=8 << 30):
+    """Smallest checkpoint spacing whose path store fits the budget (1 = keep every state)."""
+    for c in (1, 2, 4, 8, 16, 32):
+        if K * ((n_steps_lim + c - 1) // c) * d * 4 <= budget_bytes:
+            return c
+    raise L.RlsdeError(
+        f"path checkpoints for K={K}, n_steps_lim={n_steps_lim} do not fit {budget_bytes >> 30} GiB even at spacing 32; "
+        "pass a smaller n_steps_lim")
+
+
+class RolloutLoss(torch.autograd.Function):
+    """eff_loss = mean_k(-G_k - sg(G_k) S_k) as a differentiable function of the flat policy parameters.
+
+    forward launches K1 (with state checkpoints), backward launches K2; what autograd does in the
+    reference over ~25 nodes per pass (reinforce_deterministic_core.py:52-93, :240).
+    """
+
+    @staticmethod
+    def forward(ctx, flat_params, env_c, mlp_c, K, opts):
+        params_host = flat_params.detach().to("cpu", torch.float32).contiguous().numpy()
+        out = rollout_forward(env_c, mlp_c, params_host, K, store_path=True, want_logw=False, **opts)
+        st = out.stats                        # synchronises: the loss value is needed on the host anyway
+        K_global = out.cfg.K_global
+        loss = st[L.ST_SUM_LOSS] / K_global
+        ctx.env_c, ctx.mlp_c, ctx.params_host, ctx.out = env_c, mlp_c, params_host, out
+        ctx.noise = opts.get("noise")
+        ctx.device = opts.get("device")
+        ctx.K_global = K_global
+        return torch.tensor(loss, dtype=torch.float32, device=flat_params.device)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g = rollout_backward(ctx.env_c, ctx.mlp_c, ctx.params_host, ctx.out, 1.0 / ctx.K_global, noise=ctx.noise,
+                             device=ctx.device)
+        g = g.to(grad_out.device) * grad_out.to(torch.float32)
+        return g, None, None, None, None
+
+
+def noise_fill(seed, K, d, n_pass, dt, *, traj_offset=0, pass_begin=0, device=None):
+    """Increments dB[pass, k, i] exactly as the rollout kernels generate them in-kernel."""
+    lib = L.load()
+    dev = _cuda_device(device)
+    out = torch.empty((int(n_pass), int(K), int(d)), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.rlsde_noise_fill(int(seed) & 0xFFFFFFFFFFFFFFFF, int(traj_offset), int(K), int(d), int(pass_begin),
+                                  int(n_pass), float(dt), _ptr(out), stream)
+    L.check(rc, "rlsde_noise_fill")
+    return out
+
+
+def summarize(stats, dt=None):
+    """Derived quantities from a statistics record (means over finished trajectories, population variance)."""
+    n = stats[L.ST_N]
+    nf = n - stats[L.ST_N_UNFINISHED]
+    out = {"n": int(n), "n_unfinished": int(stats[L.ST_N_UNFINISHED]), "useful_steps": float(stats[L.ST_USEFUL_STEPS]),
+           "max_hit_index": int(stats[L.ST_MAX_T])}
+    if nf > 0:
+        mg = stats[L.ST_SUM_G] / nf
+        out.update(mean_return=mg, var_return=max(stats[L.ST_SUM_G2] / nf - mg * mg, 0.0),
+                   mean_hit_index=stats[L.ST_SUM_T] / nf, mean_l2=stats[L.ST_SUM_L2] / nf,
+                   mean_stoch_int=stats[L.ST_SUM_S] / nf)
+        mw = stats[L.ST_SUM_W] / nf
+        vw = max(stats[L.ST_SUM_W2] / nf - mw * mw, 0.0)
+        out.update(is_mean=mw, is_var=vw, is_rel_error=(math.sqrt(vw) / mw if mw > 0 else float("nan")))
+    return out

@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/ by executing the UNMODIFIED reference.
+
+Run in the build container only (the reference lives at /root/reference and does not
+travel to the GPU box):
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+The reference (riberaborrell/rl-sde-is v1.0.0) is imported from /root/reference/src with
+three import stubs: a two-attribute ``rl_sde_is.config`` module and
+MagicMock stand-ins for matplotlib / shapely, which are not installed and are not on the hot
+path.  Nothing of the reference is copied: we only call its public functions and record
+their inputs (the Brownian increments they draw) and outputs.
+
+Fixtures (all arrays little-endian, names are the keys of the .npz):
+
+  rollout_torch_1d.npz   reference ``sample_loss_vectorized`` (reinforce_deterministic_core.py:30-93)
+                         + ``eff_loss.backward()`` on DoubleWellStoppingTime1D, noise recorded from
+                         ``env.step_torch`` (environments.py:201-226).  Two cases (``a_*``, ``b_*``).
+  rollout_torch_2d.npz   same on DoubleWellStoppingTime2D (environments_2d.py:184-205).
+  rollout_numpy_1d.npz   reference ``test_policy_vectorized`` / ``estimate_fht_vectorized``
+                         (approximate_methods.py:577-695), noise recorded from ``env.step``.
+  rollout_numpy_2d.npz   same on the 2-D env.
+  env_step.npz           single ``env.step`` / ``env.step_torch`` calls, both reward types.
+  reinforce_iters.npz    three ``zero_grad -> loss -> backward -> Adam.step`` iterations
+                         (reinforce_deterministic_core.py:234-243) with recorded noise.
+  tables.npz             ``compute_r_table`` / ``compute_p_tensor_batch`` (dynamic_programming.py:3-36):
+                         full tensors at h=0.1, strided sub-sample + checksums at h=0.01, and a
+                         (alpha, beta) = (1, 4) case.
+"""
+import hashlib
+import os
+import sys
+import tempfile
+import time
+import types
+from unittest.mock import MagicMock
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+REF_SRC = os.environ.get("RLSDE_REFERENCE_SRC", "/root/reference/src")
+OUT_DIR = os.path.dirname(os.path.abspath(__file__))
+
+
+def import_reference():
+    for name in ["matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.colors", "shapely", "shapely.geometry"]:
+        sys.modules.setdefault(name, MagicMock())
+    tmp = tempfile.mkdtemp(prefix="rlsde_ref_")
+    cfg = types.ModuleType("rl_sde_is.config")
+    cfg.PROJECT_ROOT_DIR = tmp
+    cfg.DATA_ROOT_DIR = os.path.join(tmp, "data")
+    sys.modules["rl_sde_is.config"] = cfg
+    if REF_SRC not in sys.path:
+        sys.path.insert(0, REF_SRC)
+    import rl_sde_is.environments as env1
+    import rl_sde_is.environments_2d as env2
+    import rl_sde_is.reinforce_deterministic_core as core
+    import rl_sde_is.approximate_methods as am
+    import rl_sde_is.dynamic_programming as dp
+    import rl_sde_is.tabular_dp_tables as tdt
+    return env1, env2, core, am, dp, tdt
+
+
+def flat_params(model):
+    return {k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
+
+
+def put_params(out, prefix, model):
+    for k, v in flat_params(model).items():
+        out[f"{prefix}param.{k}"] = v
+
+
+class NoiseRecorder:
+    """Wraps env.step / env.step_torch and records the 4th return value (dbt)."""
+
+    def __init__(self, env, which):
+        self.env, self.which, self.noise = env, which, []
+        self.orig = getattr(env, which)
+
+    def __enter__(self):
+        def wrapped(*a, **kw):
+            res = self.orig(*a, **kw)
+            dbt = res[3]
+            self.noise.append(dbt.detach().numpy().copy() if torch.is_tensor(dbt) else np.array(dbt, copy=True))
+            return res
+        setattr(self.env, self.which, wrapped)
+        return self
+
+    def __exit__(self, *exc):
+        setattr(self.env, self.which, self.orig)
+
+    def stacked(self):
+        return np.stack(self.noise, axis=0).astype(np.float32)
+
+
+def torch_rollout_case(core, env, model, K, seed, out, prefix):
+    torch.manual_seed(seed)
+    model.zero_grad()
+    with NoiseRecorder(env, "step_torch") as rec:
+        loss, return_fht, time_steps = core.sample_loss_vectorized(env, model, K)
+    loss.backward()
+    out[prefix + "noise"] = rec.stacked()
+    out[prefix + "loss"] = np.array(loss.detach().numpy())
+    out[prefix + "return_fht"] = return_fht.copy()
+    out[prefix + "time_steps"] = time_steps.copy()
+    put_params(out, prefix, model)
+    for k, p in model.named_parameters():
+        out[f"{prefix}grad.{k}"] = p.grad.detach().numpy().copy()
+    out[prefix + "env"] = np.array([env.d, float(np.ravel(env.alpha)[0]), env.beta, env.dt], dtype=np.float64)
+    print(f"  {prefix}: K={K} passes={len(rec.noise)} loss={float(loss):.10f} T={time_steps[:8]}")
+
+
+def numpy_rollout_case(am, env, model, K, seed, policy_opt, out, prefix):
+    np.random.seed(seed)
+    with NoiseRecorder(env, "step") as rec:
+        res = am.test_policy_vectorized(env, model, batch_size=K, policy_opt=policy_opt)
+    out[prefix + "noise"] = rec.stacked()
+    out[prefix + "result"] = np.array(res, dtype=np.float64)
+    out[prefix + "policy_opt"] = policy_opt
+    put_params(out, prefix, model)
+    out[prefix + "env"] = np.array([env.d, float(np.ravel(env.alpha)[0]), env.beta, env.dt, env.h_state], dtype=np.float64)
+    print(f"  {prefix}: K={K} passes={len(rec.noise)} result={res}")
+    np.random.seed(seed)
+    with NoiseRecorder(env, "step") as rec2:
+        fht = am.estimate_fht_vectorized(env, model, batch_size=K)
+    assert np.array_equal(rec2.stacked(), out[prefix + "noise"])
+    out[prefix + "fht"] = np.array(fht, dtype=np.float64)
+
+
+def main():
+    t_start = time.time()
+    env1, env2, core, am, dp, tdt = import_reference()
+    torch.set_num_threads(1)
+
+    # ---------------------------------------------------------------- torch path, 1-D
+    out = {}
+    env = env1.DoubleWellStoppingTime1D(beta=1.0, alpha=1.0, dt=0.005)
+    torch.manual_seed(3)
+    model = core.DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    model.policy[4].bias.data.fill_(1.0)
+    torch_rollout_case(core, env, model, 8, 7, out, "a_")        # SURVEY Appendix D recipe
+    assert abs(float(out["a_loss"]) - 0.7900703549385071) < 1e-12, float(out["a_loss"])
+    torch.manual_seed(1)
+    model = core.DeterministicPolicy(1, 1, [32, 32], nn.Tanh())  # near-null initial policy: long paths
+    torch_rollout_case(core, env, model, 6, 11, out, "b_")
+    envb4 = env1.DoubleWellStoppingTime1D(beta=2.0, alpha=0.5, dt=0.01)
+    torch.manual_seed(5)
+    model = core.DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    model.policy[4].bias.data.fill_(0.5)
+    torch_rollout_case(core, envb4, model, 12, 13, out, "c_")
+    np.savez_compressed(os.path.join(OUT_DIR, "rollout_torch_1d.npz"), **out)
+
+    # ---------------------------------------------------------------- torch path, 2-D
+    out = {}
+    env = env2.DoubleWellStoppingTime2D(beta=1.0, alpha=1.0, dt=0.005)
+    torch.manual_seed(4)
+    model = core.DeterministicPolicy(2, 2, [32, 32], nn.Tanh())
+    model.policy[4].bias.data.fill_(1.5)
+    torch_rollout_case(core, env, model, 6, 9, out, "a_")
+    np.savez_compressed(os.path.join(OUT_DIR, "rollout_torch_2d.npz"), **out)
+
+    # ---------------------------------------------------------------- numpy path, 1-D / 2-D
+    out = {}
+    env = env1.DoubleWellStoppingTime1D(beta=1.0, alpha=1.0, dt=0.005)
+    env.discretize_state_space(0.05)
+    policy_opt = (1.5 * np.cos(env.state_space_h) + 0.25).reshape(-1, 1)      # any table: only its lookup is tested
+    torch.manual_seed(3)
+    model = core.DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    model.policy[4].bias.data.fill_(1.0)
+    numpy_rollout_case(am, env, model, 16, 21, policy_opt, out, "a_")
+    torch.manual_seed(1)
+    model = core.DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    numpy_rollout_case(am, env, model, 5, 22, np.zeros((env.n_states, 1)), out, "b_")
+    np.savez_compressed(os.path.join(OUT_DIR, "rollout_numpy_1d.npz"), **out)
+
+    # ---------------------------------------------------------------- single env steps
+    out = {}
+    rng = np.random.default_rng(0)
+    env = env1.DoubleWellStoppingTime1D(beta=1.0, alpha=1.0, dt=0.005)
+    states = rng.uniform(-2, 2.2, (64, 1)).astype(np.float32)
+    actions = rng.uniform(-3, 3, (64, 1)).astype(np.float32)
+    out["states1"], out["actions1"] = states, actions
+    for rt in ["state-action", "state-action-next-state"]:
+        tag = rt.replace("-", "_")
+        np.random.seed(5)
+        ns, r, done, dbt = env.step(states, actions, reward_type=rt)
+        out[f"np1_{tag}_next"], out[f"np1_{tag}_r"], out[f"np1_{tag}_done"], out[f"np1_{tag}_dbt"] = ns, r, done, dbt
+        torch.manual_seed(5)
+        ns, r, done, dbt = env.step_torch(torch.from_numpy(states), torch.from_numpy(actions), reward_type=rt)
+        out[f"th1_{tag}_next"], out[f"th1_{tag}_r"], out[f"th1_{tag}_done"], out[f"th1_{tag}_dbt"] = \
+            ns.numpy(), r.numpy(), done.numpy(), dbt.numpy()
+    env = env2.DoubleWellStoppingTime2D(beta=1.0, alpha=1.0, dt=0.005)
+    states = rng.uniform(-2, 2.2, (64, 2)).astype(np.float32)
+    states[:8] = np.abs(states[:8]) + 0.9
+    actions = rng.uniform(-3, 3, (64, 2)).astype(np.float32)
+    out["states2"], out["actions2"] = states, actions
+    np.random.seed(6)
+    ns, r, done, dbt = env.step(states, actions)
+    out["np2_next"], out["np2_r"], out["np2_done"], out["np2_dbt"] = ns, r, done, dbt
+    torch.manual_seed(6)
+    ns, r, done, dbt = env.step_torch(torch.from_numpy(states), torch.from_numpy(actions))
+    out["th2_next"], out["th2_r"], out["th2_done"], out["th2_dbt"] = ns.numpy(), r.numpy(), done.numpy(), dbt.numpy()
+    np.savez_compressed(os.path.join(OUT_DIR, "env_step.npz"), **out)
+
+    # ---------------------------------------------------------------- REINFORCE iterations
+    out = {}
+    env = env1.DoubleWellStoppingTime1D(beta=1.0, alpha=1.0, dt=0.005)
+    torch.manual_seed(3)
+    model = core.DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    model.policy[4].bias.data.fill_(1.0)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    put_params(out, "it0_", model)
+    torch.manual_seed(17)
+    for it in range(3):
+        opt.zero_grad()
+        with NoiseRecorder(env, "step_torch") as rec:
+            loss, ret, ts = core.sample_loss_vectorized(env, model, 8)
+        loss.backward()
+        opt.step()
+        out[f"it{it}_noise"] = rec.stacked()
+        out[f"it{it}_loss"] = np.array(loss.detach().numpy())
+        out[f"it{it}_return_fht"] = ret.copy()
+        out[f"it{it}_time_steps"] = ts.copy()
+        put_params(out, f"it{it + 1}_", model)
+        print(f"  reinforce it{it}: loss={float(loss):.8f} passes={len(rec.noise)}")
+    np.savez_compressed(os.path.join(OUT_DIR, "reinforce_iters.npz"), **out)
+
+    # ---------------------------------------------------------------- tables
+    out = {}
+
+    def table_case(tag, alpha, beta, h_state, h_action, full, stride=None):
+        env = env1.DoubleWellStoppingTime1D(beta=beta, alpha=alpha, dt=0.005)
+        env.set_action_space_bounds()
+        env.discretize_state_space(h_state)
+        env.discretize_action_space(h_action)
+        t0 = time.time()
+        R = dp.compute_r_table(env)
+        P = dp.compute_p_tensor_batch(env)
+        ok = tdt.check_p_tensor(env, P)
+        print(f"  tables {tag}: P{P.shape} R{R.shape} check={ok} {time.time() - t0:.1f}s")
+        out[f"{tag}_cfg"] = np.array([alpha, beta, env.dt, h_state, h_action], dtype=np.float64)
+        out[f"{tag}_state_grid"] = env.state_space_h
+        out[f"{tag}_action_grid"] = env.action_space_h
+        out[f"{tag}_is_in_ts"] = env.is_in_ts
+        out[f"{tag}_check"] = np.array(bool(ok))
+        out[f"{tag}_R"] = R
+        out[f"{tag}_P_sum"] = np.array(P.sum())
+        out[f"{tag}_P_sumsq"] = np.array((P * P).sum())
+        out[f"{tag}_P_colsum_maxdev"] = np.array(np.abs(P.sum(axis=0) - 1).max())
+        out[f"{tag}_P_sha256"] = np.frombuffer(hashlib.sha256(P.tobytes()).digest(), dtype=np.uint8)
+        out[f"{tag}_R_sha256"] = np.frombuffer(hashlib.sha256(R.tobytes()).digest(), dtype=np.uint8)
+        if full:
+            out[f"{tag}_P"] = P
+        else:
+            out[f"{tag}_P_stride"] = np.array(stride)
+            out[f"{tag}_P_sub"] = P[::stride[0], ::stride[1], ::stride[2]].copy()
+            out[f"{tag}_P_s100"] = P[:, 100, :].copy()      # all next-states/actions from the initial state x=-1
+
+    table_case("h01", 1.0, 1.0, 0.1, 0.1, full=True)
+    assert hashlib.sha256(out["h01_P"].tobytes()).hexdigest()[:16] == "53031080f5d0ce25"
+    table_case("b4", 1.0, 4.0, 0.1, 0.5, full=True)
+    table_case("h001", 1.0, 1.0, 0.01, 0.01, full=False, stride=(10, 10, 20))
+    np.savez_compressed(os.path.join(OUT_DIR, "tables.npz"), **out)
+
+    # 2-D numpy path last (long hitting times uncontrolled; use a drifting policy)
+    out = {}
+    env = env2.DoubleWellStoppingTime2D(beta=1.0, alpha=1.0, dt=0.005)
+    env.h_state = 0.1
+    torch.manual_seed(4)
+    model = core.DeterministicPolicy(2, 2, [32, 32], nn.Tanh())
+    model.policy[4].bias.data.fill_(1.5)
+    np.random.seed(31)
+    with NoiseRecorder(env, "step") as rec:
+        fht = am.estimate_fht_vectorized(env, model, batch_size=6)
+    out["a_noise"] = rec.stacked()
+    out["a_fht"] = np.array(fht, dtype=np.float64)
+    put_params(out, "a_", model)
+    out["a_env"] = np.array([env.d, 1.0, env.beta, env.dt], dtype=np.float64)
+    print(f"  numpy 2d fht={fht} passes={len(rec.noise)}")
+    np.savez_compressed(os.path.join(OUT_DIR, "rollout_numpy_2d.npz"), **out)
+
+    for f in sorted(os.listdir(OUT_DIR)):
+        if f.endswith(".npz"):
+            print(f"{f}: {os.path.getsize(os.path.join(OUT_DIR, f)) / 1024:.1f} KiB")
+    print(f"done in {time.time() - t_start:.1f}s  (numpy {np.__version__}, torch {torch.__version__})")
+
+
+if __name__ == "__main__":
+    main()
