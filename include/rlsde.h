@@ -70,8 +70,9 @@ typedef enum rlsde_status {
 #define RLSDE_F_STATE_F64 (1u << 3)      /* numpy-path arithmetic: f64 state and accumulators, f32 policy
                                             (SURVEY App. A-5); G/S/l2/logw outputs are double* */
 #define RLSDE_F_STORE_PATH (1u << 4)     /* write X_k checkpoints (needed by rlsde_rollout_bwd) */
-#define RLSDE_F_GRAD_F32 (1u << 5)       /* rlsde_env_step with RLSDE_F_STATE_F64: evaluate grad V in float32, as numpy
-                                            does when the 1-D env is handed a float32 state */
+#define RLSDE_F_GRAD_F32 (1u << 5)       /* rlsde_env_step with RLSDE_F_STATE_F64: the caller's state array was float32.  numpy then
+                                            evaluates grad V in float32 in the 1-D env (python-float alpha), and state**2 - 1 in
+                                            float32 in the d-D env (float64 alpha array)   */
 
 /* environment: overdamped Langevin dX = (-grad V + sigma u) dt + sigma dW,
    V(x) = sum_i alpha_i (x_i^2 - 1)^2   (environments.py:42-46, environments_2d.py:44-54) */

@@ -159,9 +159,12 @@ __global__ void env_step_kernel(StepArgs A) {
       const double xi = (double)x[i];
       // a float32 state handed to the 1-D numpy env gives a float32 gradient (python-float alpha is a weak scalar)
       double g;
-      if (A.grad_f32) {
+      if (A.grad_f32 && d == 1) {
         const float xs = (float)xi;
         g = (double)__fmul_rn(__fmul_rn(A.c4a_f[i], xs), __fsub_rn(__fmul_rn(xs, xs), 1.0f));
+      } else if (A.grad_f32) {   // d-D env: 4 * alpha (f64 array) * state (f32) * (state**2 - 1) (f32)
+        const float xs = (float)xi;
+        g = __dmul_rn(__dmul_rn(A.c4a_d[i], xi), (double)__fsub_rn(__fmul_rn(xs, xs), 1.0f));
       } else {
         g = __dmul_rn(__dmul_rn(A.c4a_d[i], xi), __dsub_rn(__dmul_rn(xi, xi), 1.0));
       }

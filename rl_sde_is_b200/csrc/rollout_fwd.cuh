@@ -235,6 +235,10 @@ __global__ void __launch_bounds__(128) rollout_fwd_kernel(const __grid_constant_
               // numpy 1-D: the first pass sees a float32 state and a python-float alpha -> float32 gradient
               const float xs = (float)xi;
               g = (double)__fmul_rn(__fmul_rn(A.c4a_f[i], xs), __fsub_rn(__fmul_rn(xs, xs), 1.0f));
+            } else if (k == 0) {
+              // numpy d-D: float64 alpha array, but state**2 - 1 is still float32 on the first pass
+              const float xs = (float)xi;
+              g = __dmul_rn(__dmul_rn(A.c4a_d[i], xi), (double)__fsub_rn(__fmul_rn(xs, xs), 1.0f));
             } else {
               g = __dmul_rn(__dmul_rn(A.c4a_d[i], xi), __dsub_rn(__dmul_rn(xi, xi), 1.0));
             }

@@ -58,9 +58,9 @@ __global__ void __launch_bounds__(128) tables_kernel(const double* __restrict__ 
   const double sd = __dmul_rn(sigma, sqrt(dt));
   double lo = ndtr(__ddiv_rn(__dsub_rn(__dsub_rn(sgrid[sp0], h), mu), sd));
   for (long long sp = sp0; sp < sp1; ++sp, out += stride) {
-    // upper edge of cell sp = lower edge of cell sp+1 (x_{sp+1} - h); the last cell of the tile /
-    // of the grid uses its own x_sp + h
-    const double edge = (sp + 1 < sp1) ? __dsub_rn(sgrid[sp + 1], h) : __dadd_rn(sgrid[sp], h);
+    // upper edge of cell sp = lower edge of cell sp+1 (x_{sp+1} - h), so each cell boundary has ONE value
+    // whatever the tiling / slab; only the last cell of the grid uses its own x_sp + h
+    const double edge = (sp + 1 < Ns) ? __dsub_rn(sgrid[sp + 1], h) : __dadd_rn(sgrid[sp], h);
     const double hi = ndtr(__ddiv_rn(__dsub_rn(edge, mu), sd));
     double p = hi - lo;
     if (sp == 0) p += lo;                 // left tail folded into the first row

@@ -84,7 +84,7 @@ class _DoubleWellBase:
     def _device_step(self, state, action, f64, hit_rule, reward_type, dbt):
         lib = L.load()
         in_dtype = state.dtype if not torch.is_tensor(state) else None
-        grad_f32 = f64 and self.d == 1 and in_dtype == np.float32 and not isinstance(self.alpha, np.ndarray)
+        grad_f32 = f64 and in_dtype == np.float32      # numpy promotion with a float32 state array
         dev = _cuda_device(None)
         K = int(state.shape[0])
         real = torch.float64 if f64 else torch.float32

@@ -1,0 +1,158 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/rlsde.h declares, argument
+validation works without a GPU, and the host-side logic (grids, policy container, sharding) is right."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from rl_sde_is_b200 import _lib as L
+from rl_sde_is_b200 import distributed as D
+from rl_sde_is_b200.models import DeterministicPolicy
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "rlsde.h")).read()
+    declared = sorted(set(re.findall(r"\b(rlsde_[a-z_0-9]+)\s*\(", header)))
+    assert declared == sorted(L.EXPORTED_SYMBOLS)
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert L.load().rlsde_version() == 100
+
+
+def test_argument_validation_without_gpu():
+    lib = L.load()
+    assert lib.rlsde_supported(1, 32, 2) == 1 and lib.rlsde_supported(1, 48, 2) == 0 and lib.rlsde_supported(1, 32, 3) == 0
+    assert lib.rlsde_param_count(L.make_mlp(1, 32)) == 1153
+    assert lib.rlsde_param_count(L.make_mlp(10, 32)) == 1738
+    assert lib.rlsde_workspace_bytes(100) > 0
+    assert lib.rlsde_strerror(-2).decode().startswith("no fused kernel")
+    env = L.make_env(1, 1.0, np.sqrt(2.0), 0.005, 1.0, 2.0, [-1.0], L.HIT_ALL_GE_LB)
+    cfg = L.RlsdeRolloutCfg()
+    cfg.K, cfg.n_steps_lim = 8, 100
+    # unsupported shape and null pointers are rejected before any CUDA call
+    assert lib.rlsde_rollout_fwd(env, L.make_mlp(1, 48), None, cfg, *([None] * 9), None, 0, None) == -2
+    assert lib.rlsde_rollout_fwd(env, L.make_mlp(1, 32), None, cfg, *([None] * 9), None, 0, None) == -1
+    assert lib.rlsde_tables(None, 4, None, 4, None, 1, 1.0, 1.0, 0.1, 0.1, 1.0, 2.0, 0, 4, None, None, None) == -1
+    assert lib.rlsde_noise_fill(0, 0, 4, 99, 0, 1, 0.1, None, None) == -1
+
+
+def test_product_path_fails_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from rl_sde_is_b200.environments import DoubleWellStoppingTime1D
+    from rl_sde_is_b200.reinforce_deterministic_core import sample_loss_vectorized
+    env = DoubleWellStoppingTime1D()
+    model = DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    with pytest.raises(L.RlsdeError):
+        sample_loss_vectorized(env, model, 4)
+
+
+def test_no_product_module_imports_the_oracle():
+    pkg = os.path.join(ROOT, "rl_sde_is_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_policy_container_layout_and_init():
+    torch.manual_seed(3)
+    m = DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    sd = m.state_dict()
+    assert list(sd) == ["policy.0.weight", "policy.0.bias", "policy.2.weight", "policy.2.bias", "policy.4.weight", "policy.4.bias"]
+    assert [tuple(v.shape) for v in sd.values()] == [(32, 1), (32,), (32, 32), (32,), (1, 32), (1,)]
+    assert sd["policy.4.weight"].abs().max() <= 5e-3 and sd["policy.4.bias"].abs().max() <= 5e-3
+
+
+def test_policy_init_matches_reference_draws(golden):
+    """Same torch seed -> the same parameters as the reference's DeterministicPolicy (fixture a_ of the torch rollouts
+    was built with torch.manual_seed(3), head bias then set to 1.0)."""
+    g = golden("rollout_torch_1d")
+    torch.manual_seed(3)
+    m = DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    m.policy[4].bias.data.fill_(1.0)
+    for k, v in m.state_dict().items():
+        assert np.array_equal(v.numpy(), g["a_param." + k]), k
+
+
+def test_grids_match_reference(golden):
+    from rl_sde_is_b200.environments import DoubleWellStoppingTime1D
+    g = golden("tables")
+    for tag in ("h01", "b4", "h001"):
+        alpha, beta, dt, hs, ha = g[tag + "_cfg"]
+        env = DoubleWellStoppingTime1D(beta=beta, alpha=alpha, dt=dt)
+        env.set_action_space_bounds()
+        env.discretize_state_space(hs)
+        env.discretize_action_space(ha)
+        assert np.array_equal(env.state_space_h, g[tag + "_state_grid"])
+        assert np.array_equal(env.action_space_h, g[tag + "_action_grid"])       # raw arange values, not rounded
+        assert np.array_equal(env.is_in_ts, g[tag + "_is_in_ts"])
+    assert env.n_states == 401 and env.n_actions == 601 and env.ts_idx.size == 101 and env.lb_idx == 300
+    assert list(env.state_init_idx) == [100] and list(env.null_action_idx) == [300]
+
+
+def test_state_index_lookup_is_within_one_cell():
+    """The reference's own test of the discretisation (tests/test_environments.py:44-57)."""
+    from rl_sde_is_b200.environments import DoubleWellStoppingTime1D
+    env = DoubleWellStoppingTime1D()
+    env.discretize_state_space(0.1)
+    x = np.random.default_rng(0).uniform(-2, 2, (1000, 1))
+    idx = env.get_state_idx(x)
+    assert (np.abs(x[:, 0] - env.state_space_h[idx]) <= 0.1).all()
+
+
+def test_shard_bounds_partition():
+    for K, W in [(10, 3), (1000000, 8), (7, 8), (100, 1)]:
+        edges = [D.shard_bounds(K, r, W) for r in range(W)]
+        assert edges[0][0] == 0 and edges[-1][1] == K
+        assert all(edges[i][1] == edges[i + 1][0] for i in range(W - 1))
+        assert max(e - b for b, e in edges) - min(e - b for b, e in edges) <= 1
+
+
+def test_ckpt_spacing_choice():
+    from rl_sde_is_b200.rollout import choose_ckpt_every
+    assert choose_ckpt_every(100, 1, 10**6) == 1
+    assert choose_ckpt_every(10**4, 1, 10**6) == 8
+    with pytest.raises(L.RlsdeError):
+        choose_ckpt_every(10**7, 10, 10**6)
+
+
+def _gloo_worker(rank, world, port, K_global, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    sh = D.Shard.from_env(K_global)
+    # each rank contributes the "gradient" and "statistics" of its shard; the packed all-reduce must give the
+    # same result as a single rank holding the whole batch
+    ids = torch.arange(sh.traj_offset, sh.traj_offset + sh.K_local, dtype=torch.float64)
+    grad = torch.stack([ids.sum(), (ids ** 2).sum(), torch.tensor(float(sh.K_local), dtype=torch.float64)]).to(torch.float32)
+    stats = torch.zeros(L.RLSDE_NSTATS, dtype=torch.float64)
+    stats[L.ST_N] = sh.K_local
+    stats[L.ST_SUM_G] = ids.sum()
+    buf = sh.all_reduce_sum(D.pack_grad_and_stats(grad, stats))
+    g, s = D.unpack_grad_and_stats(buf, 3)
+    q.put((rank, sh.traj_offset, sh.K_local, g.tolist(), float(s[L.ST_N]), float(s[L.ST_SUM_G])))
+    dist.destroy_process_group()
+
+
+def test_packed_allreduce_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    K_global, port = 101, 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, K_global, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[2] for r in res] == [51, 50] and [r[1] for r in res] == [0, 51]
+    ids = np.arange(K_global, dtype=np.float64)
+    for _, _, _, g, n, sg in res:
+        assert g[2] == K_global and abs(g[0] - ids.sum()) < 1e-3 and n == K_global and sg == ids.sum()

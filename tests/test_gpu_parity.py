@@ -1,0 +1,313 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference fixtures.
+
+Tolerances (BASELINE.json north_star): injected-noise trajectories within 1e-5 relative on work
+functionals, hit indices exact; tables within 1e-6 (we hold 1e-13); in-kernel RNG statistically
+indistinguishable (and, against the C restatement of the same Philox stream, per-trajectory close).
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import c_oracle
+from oracle import reference_semantics as ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _env(npz, p):
+    e = npz[p + "env"]
+    return int(e[0]), float(e[1]), float(e[2]), float(e[3])
+
+
+def _make_env(d, alpha, beta, dt):
+    from rl_sde_is_b200.environments import DoubleWellStoppingTime1D, DoubleWellStoppingTimeND
+    return DoubleWellStoppingTime1D(beta=beta, alpha=alpha, dt=dt) if d == 1 else DoubleWellStoppingTimeND(d, beta=beta, alpha=alpha, dt=dt)
+
+
+def _model_from(npz, prefix, d):
+    from rl_sde_is_b200.models import DeterministicPolicy
+    m = DeterministicPolicy(d, d, [32, 32], nn.Tanh())
+    m.load_state_dict({k: torch.from_numpy(np.array(npz[f"{prefix}param.{k}"])) for k in ref.PARAM_KEYS})
+    return m
+
+
+# ------------------------------------------------------------------------------ torch path, injected noise
+@pytest.mark.parametrize("fixture,prefix", [("rollout_torch_1d", "a_"), ("rollout_torch_1d", "b_"),
+                                            ("rollout_torch_1d", "c_"), ("rollout_torch_2d", "a_")])
+def test_sample_loss_vectorized_matches_reference(golden, fixture, prefix):
+    from rl_sde_is_b200.reinforce_deterministic_core import sample_loss_vectorized
+    g = golden(fixture)
+    d, alpha, beta, dt = _env(g, prefix)
+    env, model = _make_env(d, alpha, beta, dt), _model_from(g, prefix, d)
+    K = g[prefix + "noise"].shape[1]
+    loss, ret, steps = sample_loss_vectorized(env, model, K, noise=g[prefix + "noise"])
+    assert ret.dtype == np.float32 and steps.dtype == np.float64 and loss.dtype == torch.float32 and loss.dim() == 0
+    assert np.array_equal(steps, g[prefix + "time_steps"])                               # hit passes: exact
+    np.testing.assert_allclose(ret, g[prefix + "return_fht"], rtol=1e-5)
+    np.testing.assert_allclose(float(loss), float(g[prefix + "loss"]), rtol=2e-5)
+    loss.backward()
+    for k, p in model.named_parameters():
+        ref_g = g[f"{prefix}grad.{k}"]
+        scale = np.abs(ref_g).max()
+        np.testing.assert_allclose(p.grad.numpy(), ref_g, rtol=2e-4, atol=5e-4 * scale, err_msg=k)  # the reference's own f32 gradient is within ~1e-4..1e-3 of an f64 evaluation here
+
+
+def test_stochastic_integral_matches_oracle(golden):
+    from rl_sde_is_b200 import _lib as L
+    from rl_sde_is_b200 import rollout as R
+    g = golden("rollout_torch_1d")
+    for prefix in ("a_", "c_"):
+        d, alpha, beta, dt = _env(g, prefix)
+        params = ref.params_from_npz(g, prefix)
+        py = ref.rollout_loss_torch(d, alpha, beta, dt, params, g[prefix + "noise"], need_grad=False)
+        env = _make_env(d, alpha, beta, dt)
+        noise = torch.from_numpy(g[prefix + "noise"]).cuda()
+        out = R.rollout_forward(R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(d, 32), ref.flatten_params(params),
+                                noise.shape[1], noise=noise)
+        np.testing.assert_allclose(out.S.cpu().numpy(), py["stoch_int_fht"], rtol=1e-5, atol=2e-6)
+        assert np.array_equal(out.T.cpu().numpy() + 1, py["time_steps"])
+
+
+def test_checkpointed_backward_equals_full_path(golden):
+    """Gradient with state checkpoints every C passes (+ recompute) == gradient with every state kept."""
+    from rl_sde_is_b200.reinforce_deterministic_core import sample_loss_vectorized
+    g = golden("rollout_torch_1d")
+    d, alpha, beta, dt = _env(g, "a_")
+    env = _make_env(d, alpha, beta, dt)
+    grads = {}
+    for C in (1, 4, 16, 32):
+        model = _model_from(g, "a_", d)
+        loss, _, _ = sample_loss_vectorized(env, model, 8, noise=g["a_noise"], ckpt_every=C)
+        loss.backward()
+        grads[C] = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).numpy()
+    for C in (4, 16, 32):
+        # only the fp32 summation order over (trajectory, pass) changes with the segment length
+        np.testing.assert_allclose(grads[C], grads[1], rtol=1e-4, atol=1e-4 * np.abs(grads[1]).max())
+
+
+def test_reinforce_iterations_match_reference(golden):
+    """Three zero_grad -> loss -> backward -> Adam.step iterations on recorded noise follow the reference's parameters."""
+    from rl_sde_is_b200.reinforce_deterministic_core import sample_loss_vectorized
+    g = golden("reinforce_iters")
+    env = _make_env(1, 1.0, 1.0, 0.005)
+    model = _model_from(g, "it0_", 1)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    for it in range(3):
+        opt.zero_grad()
+        loss, ret, steps = sample_loss_vectorized(env, model, 8, noise=g[f"it{it}_noise"])
+        loss.backward()
+        opt.step()
+        assert np.array_equal(steps, g[f"it{it}_time_steps"])
+        np.testing.assert_allclose(float(loss), float(g[f"it{it}_loss"]), rtol=1e-4)
+        for k, v in model.state_dict().items():
+            np.testing.assert_allclose(v.numpy(), g[f"it{it + 1}_param.{k}"], rtol=0, atol=2e-4, err_msg=f"it{it} {k}")
+
+
+# ------------------------------------------------------------------------------ numpy path, injected noise
+@pytest.mark.parametrize("prefix", ["a_", "b_"])
+def test_test_policy_vectorized_matches_reference(golden, prefix):
+    from rl_sde_is_b200.approximate_methods import estimate_fht_vectorized, test_policy_vectorized
+    g = golden("rollout_numpy_1d")
+    e = g[prefix + "env"]
+    env = _make_env(1, float(e[1]), float(e[2]), float(e[3]))
+    env.discretize_state_space(float(e[4]))
+    model = _model_from(g, prefix, 1)
+    res = test_policy_vectorized(env, model, batch_size=g[prefix + "noise"].shape[1], policy_opt=g[prefix + "policy_opt"],
+                                 noise=g[prefix + "noise"])
+    want = g[prefix + "result"]
+    assert res[2] == want[2]                                                     # mean hit index: exact
+    np.testing.assert_allclose(res[0], want[0], rtol=1e-6)
+    np.testing.assert_allclose(res[1], want[1], rtol=1e-5)
+    np.testing.assert_allclose(res[3], want[3], rtol=1e-4, atol=1e-9)
+    fht = estimate_fht_vectorized(env, model, batch_size=g[prefix + "noise"].shape[1], noise=g[prefix + "noise"])
+    assert fht == float(g[prefix + "fht"])
+
+
+def test_estimate_fht_2d_matches_reference(golden):
+    from rl_sde_is_b200.approximate_methods import estimate_fht_vectorized
+    g = golden("rollout_numpy_2d")
+    d, alpha, beta, dt = _env(g, "a_")
+    fht = estimate_fht_vectorized(_make_env(d, alpha, beta, dt), _model_from(g, "a_", d), batch_size=g["a_noise"].shape[1],
+                                  noise=g["a_noise"])
+    assert fht == float(g["a_fht"])
+
+
+def test_unfinished_rollouts_return_nan(golden):
+    from rl_sde_is_b200.approximate_methods import test_policy_vectorized
+    g = golden("rollout_numpy_1d")
+    env = _make_env(1, 1.0, 1.0, 0.005)
+    env.discretize_state_space(0.05)
+    res = test_policy_vectorized(env, _model_from(g, "b_", 1), batch_size=64, k_max=5, policy_opt=np.zeros((81, 1)), seed=1)
+    assert len(res) == 4 and all(np.isnan(r) for r in res)                       # approximate_methods.py:640-643
+
+
+# ------------------------------------------------------------------------------ single passes
+def test_env_step_matches_reference(golden):
+    g = golden("env_step")
+    env = _make_env(1, 1.0, 1.0, 0.005)
+    for rt in ("state-action", "state-action-next-state"):
+        tag = rt.replace("-", "_")
+        nxt, r, done, dbt = env.step(g["states1"], g["actions1"], reward_type=rt, dbt=g[f"np1_{tag}_dbt"])
+        assert nxt.dtype == np.float64 and np.array_equal(nxt, g[f"np1_{tag}_next"])       # bit-exact
+        assert np.array_equal(r, g[f"np1_{tag}_r"]) and np.array_equal(done, g[f"np1_{tag}_done"])
+        nxt, r, done, dbt = env.step_torch(torch.from_numpy(g["states1"]), torch.from_numpy(g["actions1"]), reward_type=rt,
+                                           dbt=torch.from_numpy(g[f"th1_{tag}_dbt"]))
+        assert nxt.dtype == torch.float32 and np.array_equal(nxt.numpy(), g[f"th1_{tag}_next"])
+        assert np.array_equal(r.numpy(), g[f"th1_{tag}_r"]) and np.array_equal(done.numpy(), g[f"th1_{tag}_done"])
+    env2 = _make_env(2, 1.0, 1.0, 0.005)
+    nxt, r, done, _ = env2.step(g["states2"], g["actions2"], dbt=g["np2_dbt"])
+    assert np.array_equal(nxt, g["np2_next"]) and np.array_equal(done, g["np2_done"])
+    np.testing.assert_allclose(r, g["np2_r"], rtol=1e-7)
+    nxt, r, done, _ = env2.step_torch(torch.from_numpy(g["states2"]), torch.from_numpy(g["actions2"]), dbt=torch.from_numpy(g["th2_dbt"]))
+    assert np.array_equal(nxt.numpy(), g["th2_next"]) and np.array_equal(done.numpy(), g["th2_done"])
+    np.testing.assert_allclose(r.numpy(), g["th2_r"], rtol=3e-7)
+
+
+def test_env_step_draws_its_own_noise():
+    env = _make_env(1, 1.0, 1.0, 0.005)
+    env.rng_seed = 11
+    x = np.full((20000, 1), -1.0, dtype=np.float32)
+    _, _, _, dbt = env.step(x, np.zeros_like(x))
+    z = dbt.ravel() / np.sqrt(0.005)
+    assert abs(z.mean()) < 0.03 and abs(z.var() - 1) < 0.03
+    assert np.allclose(dbt, c_oracle.noise_fill(11, 20000, 1, 1, 0.005)[0], atol=2e-6)
+
+
+# ------------------------------------------------------------------------------ in-kernel RNG
+def test_noise_stream_matches_c_restatement():
+    from rl_sde_is_b200 import rollout as R
+    for d in (1, 2, 3, 10):
+        gpu = R.noise_fill(1234, 257, d, 37, 0.005, traj_offset=5, pass_begin=2).cpu().numpy()
+        cpu = c_oracle.noise_fill(1234, 257, d, 37, 0.005, traj_offset=5, pass_begin=2)
+        np.testing.assert_allclose(gpu, cpu, rtol=0, atol=3e-6)                   # MUFU log/sqrt/sincos vs libm
+
+
+def test_rng_rollout_equals_replay_of_its_own_noise():
+    """Philox mode == injected mode fed with rlsde_noise_fill output: the in-kernel stream is exactly the exported one."""
+    from rl_sde_is_b200 import _lib as L
+    from rl_sde_is_b200 import rollout as R
+    torch.manual_seed(1)
+    from rl_sde_is_b200.models import DeterministicPolicy
+    for d in (1, 2, 10):
+        m = DeterministicPolicy(d, d, [32, 32], nn.Tanh())
+        m.policy[4].bias.data.fill_(1.5 if d > 1 else 0.5)
+        env = _make_env(d, 1.0, 1.0, 0.005)
+        params = R.flat_parameters(m).detach().numpy()
+        K, lim = 300, 1500
+        a = R.rollout_forward(R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(d, 32), params, K, seed=99, n_steps_lim=lim)
+        noise = R.noise_fill(99, K, d, lim, 0.005)
+        b = R.rollout_forward(R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(d, 32), params, K, noise=noise, n_steps_lim=lim)
+        assert torch.equal(a.T, b.T) and torch.equal(a.G, b.G) and torch.equal(a.S, b.S)
+
+
+def test_rng_rollout_matches_c_restatement_per_trajectory():
+    from rl_sde_is_b200 import _lib as L
+    from rl_sde_is_b200 import rollout as R
+    from rl_sde_is_b200.models import DeterministicPolicy
+    torch.manual_seed(2)
+    m = DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    m.policy[4].bias.data.fill_(0.8)
+    env = _make_env(1, 1.0, 1.0, 0.005)
+    params = R.flat_parameters(m).detach().numpy()
+    K = 4096
+    out = R.rollout_forward(R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(1, 32), params, K, seed=7, n_steps_lim=4000,
+                            traj_offset=1000)
+    c = c_oracle.rollout(1, 32, params, 1.0, 1.0, 0.005, K, seed=7, n_steps_lim=4000, traj_offset=1000)
+    T, G = out.T.cpu().numpy(), out.G.cpu().numpy()
+    same = T == c["T"]
+    assert same.mean() > 0.97          # increments differ by ~1e-6 (MUFU vs libm): a few boundary crossings may move
+    np.testing.assert_allclose(G[same], c["G"][same], rtol=2e-5)
+    assert abs(G.mean() - c["G"].mean()) < 5e-3 * abs(c["G"].mean())
+
+
+def test_results_do_not_depend_on_sharding_or_batch_size():
+    from rl_sde_is_b200 import _lib as L
+    from rl_sde_is_b200 import rollout as R
+    from rl_sde_is_b200.models import DeterministicPolicy
+    torch.manual_seed(4)
+    m = DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    m.policy[4].bias.data.fill_(1.0)
+    env_c, mlp_c = R.env_struct(_make_env(1, 1.0, 1.0, 0.005), L.HIT_ALL_GE_LB), L.make_mlp(1, 32)
+    params = R.flat_parameters(m).detach().numpy()
+    full = R.rollout_forward(env_c, mlp_c, params, 30000, seed=5, n_steps_lim=3000)
+    lo = R.rollout_forward(env_c, mlp_c, params, 12345, seed=5, n_steps_lim=3000, traj_offset=0, K_global=30000)
+    hi = R.rollout_forward(env_c, mlp_c, params, 30000 - 12345, seed=5, n_steps_lim=3000, traj_offset=12345, K_global=30000)
+    assert torch.equal(full.G, torch.cat([lo.G, hi.G])) and torch.equal(full.T, torch.cat([lo.T, hi.T]))
+    again = R.rollout_forward(env_c, mlp_c, params, 30000, seed=5, n_steps_lim=3000)
+    assert np.array_equal(full.stats, again.stats)                               # deterministic reduction
+
+
+def test_importance_sampling_estimator_is_policy_independent():
+    """E^u[exp(G - S_exact)] = Psi(x0) for any control: ~0.1565 for beta = 1, dt = 0.005."""
+    from rl_sde_is_b200.approximate_methods import is_estimate
+    from rl_sde_is_b200.models import DeterministicPolicy
+    env = _make_env(1, 1.0, 1.0, 0.005)
+    vals = []
+    for bias in (0.0, 1.0):
+        torch.manual_seed(1)
+        m = DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+        m.policy[4].bias.data.fill_(bias)
+        s = is_estimate(env, m, 400000, n_steps_lim=20000, seed=3)
+        assert s["n_unfinished"] == 0
+        vals.append(s)
+        se = s["is_rel_error"] * s["is_mean"] / np.sqrt(s["n"])
+        assert abs(s["is_mean"] - 0.1565) < 5 * se + 0.002
+    assert vals[1]["is_rel_error"] < vals[0]["is_rel_error"]                     # a drift towards the target reduces variance
+    assert abs(vals[0]["mean_hit_index"] - 731.6) < 10                           # uncontrolled mean hitting pass
+
+
+def test_fast_tanh_is_statistically_equivalent():
+    from rl_sde_is_b200 import _lib as L
+    from rl_sde_is_b200 import rollout as R
+    from rl_sde_is_b200.models import DeterministicPolicy
+    torch.manual_seed(1)
+    m = DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    m.policy[4].bias.data.fill_(0.7)
+    env_c, mlp_c = R.env_struct(_make_env(1, 1.0, 1.0, 0.005), L.HIT_ALL_GE_LB), L.make_mlp(1, 32)
+    params = R.flat_parameters(m).detach().numpy()
+    a = R.summarize(R.rollout_forward(env_c, mlp_c, params, 200000, seed=8, n_steps_lim=20000).stats)
+    b = R.summarize(R.rollout_forward(env_c, mlp_c, params, 200000, seed=8, n_steps_lim=20000, tanh="fast").stats)
+    assert abs(a["mean_return"] - b["mean_return"]) < 0.01 * abs(a["mean_return"])
+    assert abs(a["mean_hit_index"] - b["mean_hit_index"]) < 0.01 * a["mean_hit_index"]
+
+
+# ------------------------------------------------------------------------------ tables
+@pytest.mark.parametrize("tag", ["h01", "b4"])
+def test_tables_match_reference(golden, tag):
+    from rl_sde_is_b200.dynamic_programming import compute_p_tensor_batch, compute_r_table
+    from rl_sde_is_b200.environments import DoubleWellStoppingTime1D
+    from rl_sde_is_b200.tabular_dp_tables import check_p_tensor
+    g = golden("tables")
+    alpha, beta, dt, hs, ha = g[tag + "_cfg"]
+    env = DoubleWellStoppingTime1D(beta=beta, alpha=alpha, dt=dt)
+    env.set_action_space_bounds()
+    env.discretize_state_space(hs)
+    env.discretize_action_space(ha)
+    P, Rt = compute_p_tensor_batch(env), compute_r_table(env)
+    assert P.dtype == np.float64 and P.shape == g[tag + "_P"].shape and P.flags["C_CONTIGUOUS"]
+    assert np.array_equal(Rt, g[tag + "_R"]) and np.signbit(Rt[env.ts_idx]).all()          # bit-exact, incl. the -0.0 rows
+    assert np.abs(P - g[tag + "_P"]).max() < 1e-13                                         # north_star asks for 1e-6
+    assert np.array_equal(P[:, env.ts_idx, :], g[tag + "_P"][:, env.ts_idx, :])
+    assert check_p_tensor(env, P)
+
+
+def test_tables_full_size_properties(golden):
+    """Config 3 (401 x 401 x 601): sub-sample and the x = -1 column against the reference, column sums, slabs."""
+    from rl_sde_is_b200.dynamic_programming import compute_p_tensor_batch
+    from rl_sde_is_b200.environments import DoubleWellStoppingTime1D
+    from rl_sde_is_b200.tabular_dp_tables import check_p_tensor
+    g = golden("tables")
+    env = DoubleWellStoppingTime1D()
+    env.set_action_space_bounds()
+    env.discretize_state_space(0.01)
+    env.discretize_action_space(0.01)
+    P = compute_p_tensor_batch(env, device_out=True)
+    assert tuple(P.shape) == (401, 401, 601) and check_p_tensor(env, P)
+    st = g["h001_P_stride"]
+    sub = P[::int(st[0]), ::int(st[1]), ::int(st[2])].cpu().numpy()
+    assert np.abs(sub - g["h001_P_sub"]).max() < 1e-13
+    assert np.abs(P[:, 100, :].cpu().numpy() - g["h001_P_s100"]).max() < 1e-13
+    assert abs(float(P.sum()) - float(g["h001_P_sum"])) < 1e-6 and abs(float((P * P).sum()) - float(g["h001_P_sumsq"])) < 1e-6
+    slab = compute_p_tensor_batch(env, device_out=True, sprime_range=(137, 259))
+    assert torch.equal(slab, P[137:259])                # a slab holds exactly the entries of the full tensor
