@@ -79,9 +79,13 @@ static int fill_cfg(const rlsde_rollout_cfg* cfg, FwdArgs& A) {
   return RLSDE_OK;
 }
 
-// workspace layout: [0, 256) work counters; [256, ...) statistics partials
-constexpr size_t WS_COUNTER_BYTES = 256;
+// workspace layout: [0, 1024) counters (32 x u64 work counters, then 64 x u32 continuation counts);
+// statistics partials; two buffers of continuation records (tail compaction); reverse-pass partials
+constexpr size_t WS_COUNTER_BYTES = 1024;
 constexpr size_t WS_STATS_BYTES = (size_t)STATS_BLOCKS * RLSDE_NSTATS * sizeof(double);
+constexpr long long WS_CONT_CAPACITY = 148LL * 16 * 128;                      // lanes of the largest forward grid
+constexpr size_t WS_CONT_REC_BYTES = 16 + 8 * (RLSDE_MAX_D + 3);              // >= sizeof(ContRec<D, F64>) for every D
+constexpr size_t WS_CONT_BYTES = 2 * (size_t)WS_CONT_CAPACITY * WS_CONT_REC_BYTES;
 
 }  // namespace rlsde
 
@@ -132,7 +136,7 @@ int64_t rlsde_param_count(const rlsde_mlp* mlp) {
 
 size_t rlsde_workspace_bytes(int64_t K) {
   (void)K;
-  return WS_COUNTER_BYTES + WS_STATS_BYTES + bwd_workspace_bytes();
+  return WS_COUNTER_BYTES + WS_STATS_BYTES + WS_CONT_BYTES + bwd_workspace_bytes();
 }
 
 int rlsde_rollout_fwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* params_host,
@@ -154,6 +158,13 @@ int rlsde_rollout_fwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
   A.noise = noise_dev; A.policy_opt = policy_opt_dev;
   A.G = G_dev; A.S = S_dev; A.T = T_dev; A.l2 = l2_dev; A.logw = logw_dev; A.path = path_dev;
   A.counter = (unsigned long long*)workspace_dev;
+  A.ws_work_counters = (unsigned long long*)workspace_dev;
+  A.ws_cont_counts = (unsigned*)((char*)workspace_dev + 256);
+  if (workspace_bytes >= WS_COUNTER_BYTES + WS_STATS_BYTES + WS_CONT_BYTES) {
+    A.ws_cont_buf[0] = (unsigned char*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES;
+    A.ws_cont_buf[1] = A.ws_cont_buf[0] + (size_t)WS_CONT_CAPACITY * WS_CONT_REC_BYTES;
+    A.ws_cont_capacity = WS_CONT_CAPACITY;
+  }
   if (A.K == 0) return RLSDE_OK;
   int sm = 0;
   if ((rc = device_sm_count(&sm)) != RLSDE_OK) return rc;
@@ -196,7 +207,7 @@ int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
   if ((rc = device_sm_count(&sm)) != RLSDE_OK) return rc;
   cudaError_t e = cudaMemsetAsync(workspace_dev, 0, WS_COUNTER_BYTES, stream);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
-  float* partial = (float*)((char*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES);
+  float* partial = (float*)((char*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES + WS_CONT_BYTES);
   int lrc = -1;
 #define X(D_, H_) if (env->d == D_ && mlp->d_hidden == H_) lrc = launch_rollout_bwd<D_, H_>(params_host, A, (float)loss_scale, grad_dev, partial, sm, stream);
   RLSDE_SHAPES(X)

@@ -208,22 +208,35 @@ __device__ __forceinline__ void load_row(const float (&src)[N], float (&w)[N]) {
 template <int IN, int H, bool FAST>
 __device__ __forceinline__ void dense_tanh(const float (&Wt)[IN][H], const float (&b)[H], const float (&hin)[IN],
                                            float (&hout)[H]) {
-  u64 acc[H / 2];
-  {
-    float bb[H];
-    load_row<H>(b, bb);
+  // Outputs are produced in slabs of 16 (8 packed accumulators): the MUFU work (tanh) of one slab is
+  // independent of the FFMA2 stream of the next, so the two pipes can overlap inside one warp.
+#ifndef RLSDE_DENSE_SLAB
+#define RLSDE_DENSE_SLAB 256
+#endif
+  constexpr int SLAB = (RLSDE_DENSE_SLAB < H) ? RLSDE_DENSE_SLAB : H;   // outputs per slab (multiple of 16)
 #pragma unroll
-    for (int j = 0; j < H / 2; ++j) acc[j] = pack2(bb[2 * j], bb[2 * j + 1]);
+  for (int s0 = 0; s0 < H; s0 += SLAB) {
+    u64 acc[SLAB / 2];
+#pragma unroll
+    for (int q = 0; q < SLAB / 4; ++q) {
+      const float4 t = reinterpret_cast<const float4*>(&b[s0])[q];
+      acc[2 * q] = pack2(t.x, t.y);
+      acc[2 * q + 1] = pack2(t.z, t.w);
+    }
+#pragma unroll
+    for (int i = 0; i < IN; ++i) {
+      float w[SLAB];
+#pragma unroll
+      for (int q = 0; q < SLAB / 4; ++q) {
+        const float4 t = reinterpret_cast<const float4*>(&Wt[i][s0])[q];
+        w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+      }
+#pragma unroll
+      for (int o = 0; o < SLAB / 2; o += 8) RLSDE_FMA2X8(acc, o, hin[i], w);
+    }
+#pragma unroll
+    for (int j = 0; j < SLAB / 2; ++j) tanh_pair<FAST>(acc[j], hout[s0 + 2 * j], hout[s0 + 2 * j + 1]);
   }
-#pragma unroll
-  for (int i = 0; i < IN; ++i) {
-    float w[H];
-    load_row<H>(Wt[i], w);
-#pragma unroll
-    for (int o = 0; o < H / 2; o += 8) RLSDE_FMA2X8(acc, o, hin[i], w);
-  }
-#pragma unroll
-  for (int j = 0; j < H / 2; ++j) tanh_pair<FAST>(acc[j], hout[2 * j], hout[2 * j + 1]);
 }
 
 // a = policy(x): two tanh layers of width H (FFMA2 with broadcast activations) and a linear head

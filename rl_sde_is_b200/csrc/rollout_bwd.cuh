@@ -137,14 +137,16 @@ __global__ void __launch_bounds__(128) rollout_bwd_kernel(const __grid_constant_
 
   // persistent per-lane gradient accumulators (column `lane + 32 c` of each block)
   u64 gW2[CPL][H / 2];
-  float gb2[CPL], gb1[CPL], gW1[CPL][D], gW3[CPL][D], gb3 = 0.f;
+  // the small blocks are sums with heavy cancellation (G dB terms): their per-pass fp32 partials are added
+  // into fp64 accumulators (one conversion + DADD per accumulator per pass)
+  double gb2[CPL], gb1[CPL], gW1[CPL][D], gW3[CPL][D], gb3 = 0.0;
 #pragma unroll
   for (int c = 0; c < CPL; ++c) {
-    gb2[c] = 0.f; gb1[c] = 0.f;
+    gb2[c] = 0.0; gb1[c] = 0.0;
 #pragma unroll
     for (int j = 0; j < H / 2; ++j) gW2[c][j] = 0ull;
 #pragma unroll
-    for (int i = 0; i < D; ++i) { gW1[c][i] = 0.f; gW3[c][i] = 0.f; }
+    for (int i = 0; i < D; ++i) { gW1[c][i] = 0.0; gW3[c][i] = 0.0; }
   }
 
   bool alive = false;
@@ -219,18 +221,30 @@ __global__ void __launch_bounds__(128) rollout_bwd_kernel(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < D; ++i) vecA[lane * D + i] = a[i];
         __syncwarp();
+        {
+          float pW3[CPL][D], pb3 = 0.f;
+#pragma unroll
+          for (int c = 0; c < CPL; ++c)
+#pragma unroll
+            for (int i = 0; i < D; ++i) pW3[c][i] = 0.f;
 #pragma unroll 2
-        for (int r = 0; r < 32; ++r) {
-          float ar[D];
+          for (int r = 0; r < 32; ++r) {
+            float ar[D];
 #pragma unroll
-          for (int i = 0; i < D; ++i) ar[i] = vecA[r * D + i];
+            for (int i = 0; i < D; ++i) ar[i] = vecA[r * D + i];
 #pragma unroll
-          for (int c = 0; c < CPL; ++c) {
-            const float hv = tileB[swz<H>(r, lane + 32 * c)];
+            for (int c = 0; c < CPL; ++c) {
+              const float hv = tileB[swz<H>(r, lane + 32 * c)];
 #pragma unroll
-            for (int i = 0; i < D; ++i) gW3[c][i] = fmaf(ar[i], hv, gW3[c][i]);
+              for (int i = 0; i < D; ++i) pW3[c][i] = fmaf(ar[i], hv, pW3[c][i]);
+            }
+            if (lane < D) pb3 += vecA[r * D + lane];
           }
-          if (lane < D) gb3 += vecA[r * D + lane];
+#pragma unroll
+          for (int c = 0; c < CPL; ++c)
+#pragma unroll
+            for (int i = 0; i < D; ++i) gW3[c][i] += (double)pW3[c][i];
+          gb3 += (double)pb3;
         }
 #pragma unroll
         for (int jj = 0; jj < H / 2; ++jj) dz2[jj] = 0ull;
@@ -255,13 +269,16 @@ __global__ void __launch_bounds__(128) rollout_bwd_kernel(const __grid_constant_
       for (int q = 0; q < H / 4; ++q)
         *reinterpret_cast<ulonglong2*>(tileB + swz<H>(lane, 4 * q)) = make_ulonglong2(dz2[2 * q], dz2[2 * q + 1]);
       __syncwarp();
+      float pb2[CPL];
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) pb2[c] = 0.f;
 #pragma unroll 2
       for (int r = 0; r < 32; ++r) {
         float hv[CPL];
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
           hv[c] = tileH1[swz<H>(r, lane + 32 * c)];
-          gb2[c] += tileB[swz<H>(r, lane + 32 * c)];
+          pb2[c] += tileB[swz<H>(r, lane + 32 * c)];
         }
 #pragma unroll
         for (int q = 0; q < H / 4; q += 2) {
@@ -271,6 +288,8 @@ __global__ void __launch_bounds__(128) rollout_bwd_kernel(const __grid_constant_
           for (int c = 0; c < CPL; ++c) RLSDE_FMA2X4_REG(gW2[c], 2 * q, hv[c], w0.x, w0.y, w1.x, w1.y);
         }
       }
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) gb2[c] += (double)pb2[c];
       __syncwarp();
       // dh1 = W2^T dz2 (dot form on the input-major, pre-scaled W2t);  dz1 = dh1 (1 - h1^2), streamed
       // four at a time into tileB (the dz2 tile is dead now) while dx = W1^T dz1 accumulates on the fly
@@ -308,17 +327,32 @@ __global__ void __launch_bounds__(128) rollout_bwd_kernel(const __grid_constant_
       __syncwarp();
 
       // input block: dW1[col][i] += dz1[col] x_i, db1[col] += dz1[col]
-#pragma unroll 2
-      for (int r = 0; r < 32; ++r) {
-        float xr[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) xr[i] = vecA[r * D + i];
+      {
+        float pb1[CPL], pW1[CPL][D];
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
-          const float dv = tileB[swz<H>(r, lane + 32 * c)];
-          gb1[c] += dv;
+          pb1[c] = 0.f;
 #pragma unroll
-          for (int i = 0; i < D; ++i) gW1[c][i] = fmaf(dv, xr[i], gW1[c][i]);
+          for (int i = 0; i < D; ++i) pW1[c][i] = 0.f;
+        }
+#pragma unroll 2
+        for (int r = 0; r < 32; ++r) {
+          float xr[D];
+#pragma unroll
+          for (int i = 0; i < D; ++i) xr[i] = vecA[r * D + i];
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) {
+            const float dv = tileB[swz<H>(r, lane + 32 * c)];
+            pb1[c] += dv;
+#pragma unroll
+            for (int i = 0; i < D; ++i) pW1[c][i] = fmaf(dv, xr[i], pW1[c][i]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          gb1[c] += (double)pb1[c];
+#pragma unroll
+          for (int i = 0; i < D; ++i) gW1[c][i] += (double)pW1[c][i];
         }
       }
       __syncwarp();
@@ -351,9 +385,9 @@ __global__ void __launch_bounds__(128) rollout_bwd_kernel(const __grid_constant_
   for (int c = 0; c < CPL; ++c) {
     const int col = lane + 32 * c;
 #pragma unroll
-    for (int i = 0; i < D; ++i) { oW1[col * D + i] = gW1[c][i]; oW3[i * H + col] = gW3[c][i]; }
-    ob1[col] = gb1[c];
-    ob2[col] = gb2[c];
+    for (int i = 0; i < D; ++i) { oW1[col * D + i] = (float)gW1[c][i]; oW3[i * H + col] = (float)gW3[c][i]; }
+    ob1[col] = (float)gb1[c];
+    ob2[col] = (float)gb2[c];
 #pragma unroll
     for (int jj = 0; jj < H / 2; ++jj) {
       float lo, hi;
@@ -362,7 +396,7 @@ __global__ void __launch_bounds__(128) rollout_bwd_kernel(const __grid_constant_
       oW2[(2 * jj + 1) * H + col] = hi;
     }
   }
-  if (lane < D) ob3[lane] = gb3;
+  if (lane < D) ob3[lane] = (float)gb3;
 }
 
 template <int D, int H>

@@ -23,6 +23,9 @@
 
 namespace rlsde {
 
+template <bool F64> struct RealT { typedef float type; };
+template <> struct RealT<true> { typedef double type; };
+
 struct FwdArgs {
   // environment (both precisions are precomputed on the host the way torch / numpy round them)
   float c4a_f[RLSDE_MAX_D];     // float32(4 * alpha_i)
@@ -51,11 +54,32 @@ struct FwdArgs {
   void* l2;
   void* logw;
   float* path;
-  unsigned long long* counter;
+  unsigned long long* counter;   // work counter of THIS launch (zeroed by the host wrapper)
+  // ---- resumable rollouts (tail compaction, see rollout_fwd_inst.cuh).  A launch draws work items from
+  //      [continuation records | fresh trajectories]; when its step budget ends, live lanes dump a record.
+  const unsigned char* cont_in;        // records to resume, or nullptr
+  const unsigned* cont_count_in;       // device-side number of records in cont_in
+  unsigned char* cont_out;             // where live lanes dump their state at the deadline, or nullptr (run to completion)
+  unsigned* cont_count_out;
+  long long K_fresh;                   // fresh trajectories started by this launch (ids [0, K_fresh))
+  unsigned round_steps;                // warp iterations after which live lanes dump (0xffffffff: never)
+  unsigned drain_steps;                // iterations a warp keeps going once the work counter is seen exhausted
+  // scratch handed in by the C ABI (caller's workspace)
+  unsigned long long* ws_work_counters;
+  unsigned* ws_cont_counts;
+  unsigned char* ws_cont_buf[2];
+  long long ws_cont_capacity;          // records per buffer
 };
 
-template <bool F64> struct RealT { typedef float type; };
-template <> struct RealT<true> { typedef double type; };
+// State of an in-flight trajectory: everything a lane needs to continue it (x, accumulators, pass index).
+template <int D, bool F64>
+struct alignas(8) ContRec {
+  long long traj;
+  int k;
+  int pad;
+  typename RealT<F64>::type x[D];
+  typename RealT<F64>::type G, S, L2;
+};
 
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
@@ -84,6 +108,10 @@ __global__ void __launch_bounds__(128) rollout_fwd_kernel(const __grid_constant_
   const bool store_path = (A.flags & RLSDE_F_STORE_PATH) != 0 && A.path != nullptr;
   const bool want_l2 = (D == 1) && A.policy_opt != nullptr && A.l2 != nullptr;
   const long long lim = inject ? (A.noise_steps < A.n_steps_lim ? A.noise_steps : A.n_steps_lim) : A.n_steps_lim;
+  typedef ContRec<D, F64> Rec;
+  const long long n_cont = A.cont_count_in ? (long long)*A.cont_count_in : 0;
+  const long long n_work = n_cont + A.K_fresh;
+  unsigned deadline = A.round_steps;
 
   bool alive = false, exhausted = false;
   long long traj = 0;
@@ -98,6 +126,35 @@ __global__ void __launch_bounds__(128) rollout_fwd_kernel(const __grid_constant_
 
   for (unsigned it = 0;; ++it) {
     if ((it & (SPB - 1)) == 0) {
+      if (A.cont_out != nullptr) {
+        // every 16 iterations: has the launch run out of work items?  then finish this round soon, so that the
+        // survivors can be re-packed into dense warps by the next launch
+        if ((it & 15u) == 0 && deadline == A.round_steps) {
+          unsigned long long c = 0;
+          if (lane == 0) c = *reinterpret_cast<volatile unsigned long long*>(A.counter);
+          c = __shfl_sync(FULL, c, 0);
+          if ((long long)c >= n_work && A.drain_steps != 0xffffffffu) {
+            const unsigned dl = it + A.drain_steps;
+            deadline = dl < deadline ? dl : deadline;
+          }
+        }
+        if (it >= deadline) {
+          const unsigned live = __ballot_sync(FULL, alive);
+          if (live) {
+            unsigned base = 0;
+            const int leader = __ffs(live) - 1;
+            if (lane == leader) base = atomicAdd(A.cont_count_out, (unsigned)__popc(live));
+            base = __shfl_sync(FULL, base, leader);
+            if (alive) {
+              Rec* r = reinterpret_cast<Rec*>(A.cont_out) + (base + __popc(live & ((1u << lane) - 1u)));
+              r->traj = traj; r->k = k; r->pad = 0; r->G = G; r->S = S; r->L2 = L2;
+#pragma unroll
+              for (int i = 0; i < D; ++i) r->x[i] = x[i];
+            }
+          }
+          break;
+        }
+      }
       const unsigned need = __ballot_sync(FULL, !alive && !exhausted);
       if (need) {
         unsigned long long base = 0;
@@ -106,8 +163,15 @@ __global__ void __launch_bounds__(128) rollout_fwd_kernel(const __grid_constant_
         base = __shfl_sync(FULL, base, leader);
         if (!alive && !exhausted) {
           const long long idx = (long long)base + __popc(need & ((1u << lane) - 1u));
-          if (idx < A.K) {
-            traj = idx; k = 0; ck = 0; alive = true;
+          if (idx < n_cont) {
+            const Rec* r = reinterpret_cast<const Rec*>(A.cont_in) + idx;
+            traj = r->traj; k = r->k; G = r->G; S = r->S; L2 = r->L2; alive = true;
+#pragma unroll
+            for (int i = 0; i < D; ++i) x[i] = r->x[i];
+            const int rem = k % A.ckpt_every;
+            ck = rem ? A.ckpt_every - rem : 0;
+          } else if (idx < n_work) {
+            traj = idx - n_cont; k = 0; ck = 0; alive = true;
             G = 0; S = 0; L2 = 0;
 #pragma unroll
             for (int i = 0; i < D; ++i) x[i] = F64 ? (real)A.x0_d[i] : (real)A.x0_f[i];
