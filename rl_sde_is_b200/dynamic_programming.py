@@ -23,7 +23,7 @@ def _device_grids(env, dev):
     return sg, ag, ts
 
 
-def _tables(env, want_p, want_r, device, sprime_range=None):
+def _tables(env, want_p, want_r, device, sprime_range=None, exact_cdf=False):
     if env.d != 1:
         raise L.RlsdeError("the tabular builder covers the 1-D environment (as the reference's does)")
     lib = L.load()
@@ -31,12 +31,14 @@ def _tables(env, want_p, want_r, device, sprime_range=None):
     sg, ag, ts = _device_grids(env, dev)
     Ns, Na = int(sg.numel()), int(ag.numel())
     lo, hi = (0, Ns) if sprime_range is None else (int(sprime_range[0]), int(sprime_range[1]))
+    grid = np.asarray(env.state_space_h, dtype=np.float64)
+    uniform = int(Ns >= 2 and np.abs(grid - (grid[0] + np.arange(Ns) * (grid[-1] - grid[0]) / (Ns - 1))).max() <= 1e-14 and not exact_cdf)
     P = torch.empty((hi - lo, Ns, Na), dtype=torch.float64, device=dev) if want_p else None
     Rt = torch.empty((Ns, Na), dtype=torch.float64, device=dev) if want_r else None
     with torch.cuda.device(dev):
         rc = lib.rlsde_tables(_ptr(sg), Ns, _ptr(ag), Na, _ptr(ts), int(env.is_in_ts.sum()), float(env.alpha),
                               float(env.sigma), float(env.dt), float(env.h_state) / 2.0, float(env.lb), float(env.rb),
-                              lo, hi, _ptr(P), _ptr(Rt), torch.cuda.current_stream(dev).cuda_stream)
+                              lo, hi, _ptr(P), _ptr(Rt), uniform, torch.cuda.current_stream(dev).cuda_stream)
     L.check(rc, "rlsde_tables")
     return P, Rt
 
@@ -47,11 +49,13 @@ def compute_r_table(env, *, device=None, device_out=False):
     return Rt if device_out else Rt.cpu().numpy()
 
 
-def compute_p_tensor_batch(env, *, device=None, device_out=False, sprime_range=None):
+def compute_p_tensor_batch(env, *, device=None, device_out=False, sprime_range=None, exact_cdf=False):
     """P[s', s, a] (float64, shape (n_states, n_states, n_actions), action innermost).
 
-    ``sprime_range=(begin, end)`` builds only that slab of next-states (multi-GPU sharding)."""
-    P, _ = _tables(env, True, False, device, sprime_range)
+    ``sprime_range=(begin, end)`` builds only that slab of next-states (multi-GPU sharding).
+    ``exact_cdf=True`` forces two erf/erfc evaluations per cell edge (the reference's formula literally) instead of
+    the quadrature fast path used on fine uniform grids; both agree with the reference to < 1e-13."""
+    P, _ = _tables(env, True, False, device, sprime_range, exact_cdf)
     return P if device_out else P.cpu().numpy()
 
 
