@@ -167,11 +167,14 @@ int rlsde_rollout_fwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
  * reinforce_deterministic_core.py:91,240; recursion in SURVEY App. C).  Needs the G/T outputs
  * and the checkpoints of a forward call made with RLSDE_F_STORE_PATH and the same cfg.
  * grad_dev: float[P] in state_dict order, overwritten.  Unfinished trajectories contribute 0.
+ * order_dev: optional int64[K] permutation of the local trajectory ids giving the processing order; passing the
+ * ids sorted by decreasing T balances the lock-step lanes (trajectories are dealt round-robin in this order).  The
+ * result does not depend on it beyond fp32 summation order; NULL = identity.
  */
 int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* params_host,
                       const rlsde_rollout_cfg* cfg, const float* noise_dev, const float* G_dev,
-                      const int32_t* T_dev, const float* path_dev, double loss_scale, float* grad_dev,
-                      void* workspace_dev, size_t workspace_bytes, void* stream);
+                      const int32_t* T_dev, const float* path_dev, const int64_t* order_dev, double loss_scale,
+                      float* grad_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* Deterministic fp64 reduction of per-trajectory outputs into a statistics record. */
 int rlsde_reduce_stats(int64_t K, int64_t n_steps_lim, uint32_t flags, const void* G_dev, const void* S_dev,

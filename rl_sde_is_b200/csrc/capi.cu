@@ -186,8 +186,8 @@ int rlsde_rollout_fwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
 
 int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* params_host,
                       const rlsde_rollout_cfg* cfg, const float* noise_dev, const float* G_dev, const int32_t* T_dev,
-                      const float* path_dev, double loss_scale, float* grad_dev, void* workspace_dev,
-                      size_t workspace_bytes, void* stream_) {
+                      const float* path_dev, const int64_t* order_dev, double loss_scale, float* grad_dev,
+                      void* workspace_dev, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = check_env_mlp(env, mlp);
   if (rc != RLSDE_OK) return rc;
@@ -202,6 +202,7 @@ int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
   if ((A.flags & RLSDE_F_NOISE_INJECTED) && !noise_dev) return RLSDE_ERR_INVALID_ARG;
   A.noise = noise_dev;
   A.G = (void*)G_dev; A.T = (int*)T_dev; A.path = (float*)path_dev;
+  A.order = (const long long*)order_dev;
   A.counter = (unsigned long long*)workspace_dev;
   int sm = 0;
   if ((rc = device_sm_count(&sm)) != RLSDE_OK) return rc;

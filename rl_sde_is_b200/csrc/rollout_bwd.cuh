@@ -113,9 +113,14 @@ __device__ __forceinline__ void em_step_f32(const FwdArgs& A, float (&x)[D], con
   }
 }
 
+// Resident blocks per SM the register allocation aims for (measured on B200, d = 1, H = 32: see DESIGN.md)
+#ifndef RLSDE_BWD_MIN_BLOCKS
+#define RLSDE_BWD_MIN_BLOCKS 2
+#endif
+
 // Per-warp partial gradient layout = state_dict order: W1 (H,D), b1 (H), W2 (H,H), b2 (H), W3 (D,H), b3 (D)
 template <int D, int H, bool FAST>
-__global__ void __launch_bounds__(128) rollout_bwd_kernel(const __grid_constant__ MlpConst<D, H> W,
+__global__ void __launch_bounds__(128, RLSDE_BWD_MIN_BLOCKS) rollout_bwd_kernel(const __grid_constant__ MlpConst<D, H> W,
                                                           const __grid_constant__ FwdArgs A, float* __restrict__ partial) {
   static_assert(H == 32 || H == 64, "column-per-lane accumulation needs H in {32, 64}");
   constexpr int CPL = H / 32;                 // columns of the HxH block owned by a lane
@@ -150,7 +155,8 @@ __global__ void __launch_bounds__(128) rollout_bwd_kernel(const __grid_constant_
   }
 
   bool alive = false;
-  long long traj = gl - n_lanes;   // next static assignment: traj += n_lanes
+  long long slot = gl - n_lanes;   // next static assignment: slot += n_lanes, traj = order[slot]
+  long long traj = 0;
   int kstar = 0, seg = 0;
   float Gk = 0.f;
   float lam[D];
@@ -161,9 +167,12 @@ __global__ void __launch_bounds__(128) rollout_bwd_kernel(const __grid_constant_
   for (int i = 0; i < D; ++i) lam[i] = 0.f;
 
   for (;;) {
-    // ---- work assignment (static round robin; unfinished trajectories are skipped)
-    while (!alive && traj + n_lanes < A.K) {
-      traj += n_lanes;
+    // ---- work assignment: static round robin over `order` (trajectories sorted by length, longest first, so
+    // that the 32 lanes of a warp walk trajectories of similar length and every lane gets a similar total);
+    // static => deterministic gradients.  Unfinished trajectories are skipped.
+    while (!alive && slot + n_lanes < A.K) {
+      slot += n_lanes;
+      traj = A.order ? A.order[slot] : slot;
       const int t = A.T[traj];
       if (t >= 0) {
         alive = true; kstar = t; seg = t / C; Gk = ((const float*)A.G)[traj];

@@ -55,6 +55,7 @@ struct FwdArgs {
   void* logw;
   float* path;
   unsigned long long* counter;   // work counter of THIS launch (zeroed by the host wrapper)
+  const long long* order;        // reverse pass: processing order of the trajectories (or nullptr = identity)
   // ---- resumable rollouts (tail compaction, see rollout_fwd_inst.cuh).  A launch draws work items from
   //      [continuation records | fresh trajectories]; when its step budget ends, live lanes dump a record.
   const unsigned char* cont_in;        // records to resume, or nullptr

@@ -163,7 +163,7 @@ def rollout_forward(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=10**6, 
     return RolloutOut(G=G, S=S, T=T, l2=l2, logw=logw, path=path, stats_dev=stats, cfg=cfg)
 
 
-def rollout_backward(env_c, mlp_c, params_host, fwd: RolloutOut, loss_scale, *, noise=None, device=None):
+def rollout_backward(env_c, mlp_c, params_host, fwd: RolloutOut, loss_scale, *, noise=None, device=None, balance=True):
     """K2: gradient of loss_scale * sum_k(-G_k - sg(G_k) S_k) w.r.t. the flat parameters (float32 CUDA tensor)."""
     lib = L.load()
     dev = _cuda_device(device)
@@ -173,9 +173,11 @@ def rollout_backward(env_c, mlp_c, params_host, fwd: RolloutOut, loss_scale, *, 
     grad = torch.empty(int(lib.rlsde_param_count(mlp_c)), dtype=torch.float32, device=dev)
     ws = _workspace(dev)
     with torch.cuda.device(dev):
+        # longest trajectories first (stable sort => deterministic): balances the lock-step lanes of the reverse pass
+        order = torch.argsort(fwd.T, descending=True, stable=True) if balance and fwd.T.numel() > 32 else None
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = lib.rlsde_rollout_bwd(env_c, mlp_c, params_host.ctypes.data, fwd.cfg, _ptr(noise), _ptr(fwd.G), _ptr(fwd.T),
-                                   _ptr(fwd.path), float(loss_scale), _ptr(grad), _ptr(ws), ws.numel(), stream)
+                                   _ptr(fwd.path), _ptr(order), float(loss_scale), _ptr(grad), _ptr(ws), ws.numel(), stream)
     L.check(rc, "rlsde_rollout_bwd")
     return grad
 
