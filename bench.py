@@ -321,19 +321,48 @@ def secondary_measurements(dev):
                                     "mean_steps_it10_29": float(np.mean(data["exp_time_steps"][10:])),
                                     "reference_cpu": "0.14 it/s at it.0, ~2.4 it/s at it.10-20 (BASELINE.md, 8-core Xeon)"}
         env.set_action_space_bounds(); env.discretize_state_space(0.01); env.discretize_action_space(0.01)
-        compute_p_tensor_batch(env, device_out=True)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        P = compute_p_tensor_batch(env, device_out=True)
-        b.record()
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b)
-        nbytes = P.numel() * 8
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-        out["tables_config2"] = {"ms": ms, "bytes": nbytes, "GBps": nbytes / ms / 1e6,
-                                 "frac_of_hbm_peak": nbytes / ms / 1e6 / float(peaks.get("hbm_gbs", 6536.7)),
-                                 "reference_cpu_s": 55.3}
+        tab = {}
+        for name, exact in (("gauss_legendre", False), ("erf_erfc", True)):
+            ts = []
+            for it in range(5):
+                flush.fill_(it)                      # L2 flush between timed builds
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                P = compute_p_tensor_batch(env, device_out=True, exact_cdf=exact)
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+                nbytes = P.numel() * 8
+                del P
+            ms = float(np.median(ts[2:]))
+            tab[name] = {"ms": ms, "GBps": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / float(peaks.get("hbm_gbs", 6536.7))}
+        out["tables_config2"] = {"bytes": nbytes, **tab, "reference_cpu_s": 55.3,
+                                 "note": "P (401, 401, 601) float64 device-resident; roofline = HBM write, peak = MEASURED_PEAKS hbm_gbs"}
+        # large-batch REINFORCE loss + gradient (K1 with state checkpoints + K2), CUDA-event timed
+        from rl_sde_is_b200 import _lib as L2
+        from rl_sde_is_b200 import rollout as R2
+        env1 = DoubleWellStoppingTime1D(beta=1.0, alpha=1.0, dt=0.005)
+        m = make_policy(1)
+        m.policy[4].bias.data.fill_(0.5)
+        params = R2.flat_parameters(m).detach().numpy()
+        env_c, mlp_c = R2.env_struct(env1, L2.HIT_ALL_GE_LB), L2.make_mlp(1, 32)
+        Kt = 400000
+        for it in range(3):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            fo = R2.rollout_forward(env_c, mlp_c, params, Kt, seed=it, n_steps_lim=4000, store_path=True, ckpt_every=1, want_logw=False, device=dev)
+            e[1].record()
+            R2.rollout_backward(env_c, mlp_c, params, fo, 1.0 / Kt, device=dev)
+            e[2].record()
+            torch.cuda.synchronize()
+        u = float(fo.stats[L2.ST_USEFUL_STEPS])
+        f_ms, b_ms = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
+        out["train_large_batch"] = {"K": Kt, "useful_steps": u, "fwd_ms": f_ms, "bwd_ms": b_ms,
+                                    "train_steps_per_s": u / (f_ms + b_ms) * 1e3, "bwd_steps_per_s": u / b_ms * 1e3,
+                                    "fp32_frac_train": u / (f_ms + b_ms) * 1e3 * 6556 / 74.45e12,
+                                    "note": "6556 FLOP per useful step (forward + reverse, SURVEY 8d)"}
     except Exception as exc:
         out["secondary_error"] = repr(exc)
     return out

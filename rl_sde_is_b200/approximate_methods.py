@@ -17,7 +17,7 @@ from . import rollout as R
 from .reinforce_deterministic_core import _next_seed
 
 
-def _numpy_path_rollout(env, model, batch_size, k_max, policy_opt, *, noise, seed, tanh, state_f64, device, dist,
+def _numpy_path_rollout(env, model, batch_size, k_max, policy_opt, *, noise, seed, tanh, state_f64, device, dist, kernel="auto",
                         stoch_int="reference", want_logw=False):
     d, H = R.policy_shape(model)
     if d != env.d:
@@ -35,7 +35,7 @@ def _numpy_path_rollout(env, model, batch_size, k_max, policy_opt, *, noise, see
         if env.d != 1:
             raise L.RlsdeError("the policy l2 error lookup is defined for the 1-D state grid only (environments.py:318-321)")
         grid = (env.state_space_low, env.state_space_high, env.h_state)
-    opts = dict(seed=_next_seed(seed), n_steps_lim=int(k_max), noise=noise, tanh=tanh, state_f64=state_f64,
+    opts = dict(seed=_next_seed(seed), n_steps_lim=int(k_max), noise=noise, tanh=tanh, state_f64=state_f64, kernel=kernel,
                 policy_opt=policy_opt, grid=grid, want_logw=want_logw, stoch_int=stoch_int, device=dev)
     if dist is not None:
         opts.update(traj_offset=dist.traj_offset, K_global=dist.K_global)
@@ -47,13 +47,13 @@ def _numpy_path_rollout(env, model, batch_size, k_max, policy_opt, *, noise, see
 
 
 def test_policy_vectorized(env, model, batch_size=10, k_max=10**7, policy_opt=None, *, noise=None, seed=None,
-                           tanh="precise", state_f64=True, device=None, dist=None):
+                           tanh="precise", state_f64=True, device=None, dist=None, kernel="auto"):
     """``(mean return, var return (ddof=0), mean hit index[, mean policy l2 error])``; all-NaN if any
     trajectory has not reached the target set within ``k_max`` passes (reference :640-643).
 
     Unlike the reference (which crashes at :610-611), ``policy_opt=None`` is accepted and returns the
     3-tuple its last branch (:647-648) intends."""
-    _, st = _numpy_path_rollout(env, model, batch_size, k_max, policy_opt, noise=noise, seed=seed, tanh=tanh,
+    _, st = _numpy_path_rollout(env, model, batch_size, k_max, policy_opt, noise=noise, seed=seed, tanh=tanh, kernel=kernel,
                                 state_f64=state_f64, device=device, dist=dist)
     n_out = 4 if policy_opt is not None else 3
     if st[L.ST_N_UNFINISHED] > 0:
@@ -70,22 +70,22 @@ def test_policy_vectorized(env, model, batch_size=10, k_max=10**7, policy_opt=No
 test_policy_vectorized.__test__ = False     # not a pytest test, despite the reference's name
 
 
-def estimate_fht_vectorized(env, model, batch_size=int(1e5), k_max=10**7, *, noise=None, seed=None, tanh="precise",
+def estimate_fht_vectorized(env, model, batch_size=int(1e5), k_max=10**7, *, noise=None, seed=None, tanh="precise", kernel="auto",
                             state_f64=True, device=None, dist=None):
     """Mean first hitting time ``mean(dt * k*)`` (reference :650-695).  NaN if a trajectory is unfinished
     (the reference would average uninitialised ``np.empty`` slots)."""
-    _, st = _numpy_path_rollout(env, model, batch_size, k_max, None, noise=noise, seed=seed, tanh=tanh,
+    _, st = _numpy_path_rollout(env, model, batch_size, k_max, None, noise=noise, seed=seed, tanh=tanh, kernel=kernel,
                                 state_f64=state_f64, device=device, dist=dist)
     if st[L.ST_N_UNFINISHED] > 0:
         return np.nan
     return np.float64(env.dt * st[L.ST_SUM_T] / st[L.ST_N])
 
 
-def is_estimate(env, model, batch_size, n_steps_lim=10**7, *, noise=None, seed=None, tanh="precise", state_f64=False,
+def is_estimate(env, model, batch_size, n_steps_lim=10**7, *, noise=None, seed=None, tanh="precise", state_f64=False, kernel="auto",
                 device=None, dist=None):
     """Importance-sampling estimate of Psi(x0) = E[exp(-tau)] under the policy's change of measure
     (SURVEY App. C): weights exp(G - S_exact).  Returns a dict with the estimator mean, its relative
     error std/mean, return statistics, mean hitting index and the unfinished count."""
-    _, st = _numpy_path_rollout(env, model, batch_size, n_steps_lim, None, noise=noise, seed=seed, tanh=tanh,
+    _, st = _numpy_path_rollout(env, model, batch_size, n_steps_lim, None, noise=noise, seed=seed, tanh=tanh, kernel=kernel,
                                 state_f64=state_f64, device=device, dist=dist, stoch_int="exact", want_logw=True)
     return R.summarize(st)

@@ -9,6 +9,7 @@
 #include "../../include/rlsde.h"
 #include "aux_kernels.cuh"
 #include "rollout_bwd.cuh"
+#include "rollout_warp.cuh"
 
 namespace rlsde {
 
@@ -29,6 +30,15 @@ static bool shape_supported(int d, int H, int n_hidden) {
   RLSDE_SHAPES(X)
 #undef X
   return false;
+}
+
+// kernel family for a call: latency kernels (warp per trajectory) for small batches, throughput kernels otherwise
+static bool use_warp_kernels(const FwdArgs& A, int H, int sm_count, bool needs_all_states) {
+  if (H != WARP_H) return false;
+  if (needs_all_states && A.ckpt_every != 1) return false;
+  if (A.flags & RLSDE_F_KERNEL_THREAD) return false;
+  if (A.flags & RLSDE_F_KERNEL_WARP) return true;
+  return A.K <= warp_path_max_k(sm_count);
 }
 
 static int device_sm_count(int* sm_count) {
@@ -171,7 +181,11 @@ int rlsde_rollout_fwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
   cudaError_t e = cudaMemsetAsync(workspace_dev, 0, WS_COUNTER_BYTES, stream);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
   int lrc = -1;
-#define X(D_, H_) if (env->d == D_ && mlp->d_hidden == H_) lrc = launch_rollout_fwd<D_, H_>(params_host, A, sm, stream);
+  const bool warp_path = use_warp_kernels(A, mlp->d_hidden, sm, (A.flags & RLSDE_F_STORE_PATH) != 0);
+#define X(D_, H_)                                                                              \
+  if (env->d == D_ && mlp->d_hidden == H_)                                                     \
+    lrc = (warp_path && H_ == WARP_H) ? launch_rollout_fwd_warp<D_>(params_host, A, sm, stream) \
+                                      : launch_rollout_fwd<D_, H_>(params_host, A, sm, stream);
   RLSDE_SHAPES(X)
 #undef X
   if (lrc != 0) return cuda_fail((cudaError_t)lrc, "rollout_fwd launch");
@@ -210,7 +224,11 @@ int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
   float* partial = (float*)((char*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES + WS_CONT_BYTES);
   int lrc = -1;
-#define X(D_, H_) if (env->d == D_ && mlp->d_hidden == H_) lrc = launch_rollout_bwd<D_, H_>(params_host, A, (float)loss_scale, grad_dev, partial, sm, stream);
+  const bool warp_path = use_warp_kernels(A, mlp->d_hidden, sm, true);
+#define X(D_, H_)                                                                                                          \
+  if (env->d == D_ && mlp->d_hidden == H_)                                                                                 \
+    lrc = (warp_path && H_ == WARP_H) ? launch_rollout_bwd_warp<D_>(params_host, A, (float)loss_scale, grad_dev, partial, sm, stream) \
+                                      : launch_rollout_bwd<D_, H_>(params_host, A, (float)loss_scale, grad_dev, partial, sm, stream);
   RLSDE_SHAPES(X)
 #undef X
   if (lrc != 0) return cuda_fail((cudaError_t)lrc, "rollout_bwd launch");

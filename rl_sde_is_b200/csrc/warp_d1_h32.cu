@@ -1,0 +1,3 @@
+// warp-per-trajectory (small-batch, latency-oriented) rollout kernels for d = 1, hidden width = 32
+#include "rollout_warp_inst.cuh"
+RLSDE_INSTANTIATE_WARP(1)

@@ -32,7 +32,7 @@ def _next_seed(seed):
 
 
 def sample_loss_vectorized(env, model, K, *, noise=None, seed=None, n_steps_lim=10**6, tanh="precise",
-                           stoch_int="reference", ckpt_every=None, device=None, dist=None):
+                           stoch_int="reference", ckpt_every=None, device=None, dist=None, kernel="auto"):
     """Sample K trajectories under the policy and return ``(eff_loss, return_fht, time_steps)``.
 
     ``eff_loss`` is a 0-d float32 tensor (on the parameters' device) whose ``.backward()`` fills
@@ -55,7 +55,7 @@ def sample_loss_vectorized(env, model, K, *, noise=None, seed=None, n_steps_lim=
     if ckpt_every is None:
         ckpt_every = R.choose_ckpt_every(int(K), d, lim)
     opts = dict(seed=_next_seed(seed), n_steps_lim=n_steps_lim, noise=noise, tanh=tanh, stoch_int=stoch_int,
-                ckpt_every=ckpt_every, device=dev)
+                ckpt_every=ckpt_every, device=dev, kernel=kernel)
     if dist is not None:
         opts.update(traj_offset=dist.traj_offset, K_global=dist.K_global)
     flat = R.flat_parameters(model)

@@ -102,7 +102,7 @@ class RolloutOut:
 
 def rollout_forward(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=10**6, noise=None, traj_offset=0,
                     K_global=None, tanh="precise", stoch_int="reference", state_f64=False, store_path=False,
-                    ckpt_every=1, policy_opt=None, grid=None, want_logw=True, device=None, out=None):
+                    ckpt_every=1, policy_opt=None, grid=None, want_logw=True, device=None, out=None, kernel="auto"):
     """One launch of K1 for K trajectories.  ``params_host``: contiguous float32 numpy array (state_dict order)."""
     lib = L.load()
     dev = _cuda_device(device)
@@ -131,6 +131,9 @@ def rollout_forward(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=10**6, 
         flags |= L.F_STOCH_INT_EXACT
     elif stoch_int != "reference":
         raise L.RlsdeError("stoch_int must be 'reference' or 'exact'")
+    if kernel not in ("auto", "thread", "warp"):
+        raise L.RlsdeError("kernel must be 'auto', 'thread' or 'warp'")
+    flags |= {"auto": 0, "thread": L.F_KERNEL_THREAD, "warp": L.F_KERNEL_WARP}[kernel]
     real = torch.float64 if state_f64 else torch.float32
     if state_f64:
         flags |= L.F_STATE_F64

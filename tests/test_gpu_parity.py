@@ -33,15 +33,19 @@ def _model_from(npz, prefix, d):
 
 
 # ------------------------------------------------------------------------------ torch path, injected noise
+KERNELS = ["thread", "warp"]      # throughput kernels (trajectory per thread) / latency kernels (trajectory per warp)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("fixture,prefix", [("rollout_torch_1d", "a_"), ("rollout_torch_1d", "b_"),
                                             ("rollout_torch_1d", "c_"), ("rollout_torch_2d", "a_")])
-def test_sample_loss_vectorized_matches_reference(golden, fixture, prefix):
+def test_sample_loss_vectorized_matches_reference(golden, fixture, prefix, kernel):
     from rl_sde_is_b200.reinforce_deterministic_core import sample_loss_vectorized
     g = golden(fixture)
     d, alpha, beta, dt = _env(g, prefix)
     env, model = _make_env(d, alpha, beta, dt), _model_from(g, prefix, d)
     K = g[prefix + "noise"].shape[1]
-    loss, ret, steps = sample_loss_vectorized(env, model, K, noise=g[prefix + "noise"])
+    loss, ret, steps = sample_loss_vectorized(env, model, K, noise=g[prefix + "noise"], kernel=kernel)
     assert ret.dtype == np.float32 and steps.dtype == np.float64 and loss.dtype == torch.float32 and loss.dim() == 0
     assert np.array_equal(steps, g[prefix + "time_steps"])                               # hit passes: exact
     np.testing.assert_allclose(ret, g[prefix + "return_fht"], rtol=1e-5)
@@ -66,10 +70,11 @@ def test_stochastic_integral_matches_oracle(golden):
         py = ref.rollout_loss_torch(d, alpha, beta, dt, params, g[prefix + "noise"], need_grad=False)
         env = _make_env(d, alpha, beta, dt)
         noise = torch.from_numpy(g[prefix + "noise"]).cuda()
-        out = R.rollout_forward(R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(d, 32), ref.flatten_params(params),
-                                noise.shape[1], noise=noise)
-        np.testing.assert_allclose(out.S.cpu().numpy(), py["stoch_int_fht"], rtol=1e-5, atol=2e-6)
-        assert np.array_equal(out.T.cpu().numpy() + 1, py["time_steps"])
+        for kernel in KERNELS:
+            out = R.rollout_forward(R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(d, 32), ref.flatten_params(params),
+                                    noise.shape[1], noise=noise, kernel=kernel)
+            np.testing.assert_allclose(out.S.cpu().numpy(), py["stoch_int_fht"], rtol=1e-5, atol=2e-6)
+            assert np.array_equal(out.T.cpu().numpy() + 1, py["time_steps"])
 
 
 def test_checkpointed_backward_equals_full_path(golden):
@@ -81,7 +86,7 @@ def test_checkpointed_backward_equals_full_path(golden):
     grads = {}
     for C in (1, 4, 16, 32):
         model = _model_from(g, "a_", d)
-        loss, _, _ = sample_loss_vectorized(env, model, 8, noise=g["a_noise"], ckpt_every=C)
+        loss, _, _ = sample_loss_vectorized(env, model, 8, noise=g["a_noise"], ckpt_every=C, kernel="thread")
         loss.backward()
         grads[C] = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).numpy()
     for C in (4, 16, 32):
@@ -89,8 +94,9 @@ def test_checkpointed_backward_equals_full_path(golden):
         np.testing.assert_allclose(grads[C], grads[1], rtol=1e-4, atol=1e-4 * np.abs(grads[1]).max())
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("d", [3, 10])
-def test_loss_and_gradient_higher_dimension_match_oracle(d):
+def test_loss_and_gradient_higher_dimension_match_oracle(d, kernel):
     """d = 10 is config 4's shape; the reference has no d = 10 env, so the check is against the torch restatement
     (pinned on the reference's 1-D / 2-D fixtures) replaying the kernel's own Philox increments."""
     from rl_sde_is_b200 import rollout as R
@@ -104,7 +110,7 @@ def test_loss_and_gradient_higher_dimension_match_oracle(d):
     noise = R.noise_fill(77, K, d, lim, env.dt).cpu().numpy()
     py = ref.rollout_loss_torch(d, 1.0, 1.0, 0.005, {k: v.detach().clone() for k, v in model.state_dict().items()}, noise)
     assert py["all_hit"]
-    loss, ret, steps = sample_loss_vectorized(env, model, K, seed=77, n_steps_lim=lim)      # in-kernel Philox
+    loss, ret, steps = sample_loss_vectorized(env, model, K, seed=77, n_steps_lim=lim, kernel=kernel)      # in-kernel Philox
     assert np.array_equal(steps, py["time_steps"].astype(np.float64))
     np.testing.assert_allclose(ret, py["return_fht"], rtol=1e-5)
     np.testing.assert_allclose(float(loss.detach()), float(py["loss"]), rtol=5e-5)
@@ -114,7 +120,8 @@ def test_loss_and_gradient_higher_dimension_match_oracle(d):
         np.testing.assert_allclose(p.grad.numpy(), py["grads"][k], rtol=2e-4, atol=5e-4 * gscale, err_msg=k)
 
 
-def test_reinforce_iterations_match_reference(golden):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_reinforce_iterations_match_reference(golden, kernel):
     """Three zero_grad -> loss -> backward -> Adam.step iterations on recorded noise follow the reference's parameters."""
     from rl_sde_is_b200.reinforce_deterministic_core import sample_loss_vectorized
     g = golden("reinforce_iters")
@@ -123,7 +130,7 @@ def test_reinforce_iterations_match_reference(golden):
     opt = torch.optim.Adam(model.parameters(), lr=1e-2)
     for it in range(3):
         opt.zero_grad()
-        loss, ret, steps = sample_loss_vectorized(env, model, 8, noise=g[f"it{it}_noise"])
+        loss, ret, steps = sample_loss_vectorized(env, model, 8, noise=g[f"it{it}_noise"], kernel=kernel)
         loss.backward()
         opt.step()
         assert np.array_equal(steps, g[f"it{it}_time_steps"])
@@ -133,8 +140,9 @@ def test_reinforce_iterations_match_reference(golden):
 
 
 # ------------------------------------------------------------------------------ numpy path, injected noise
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("prefix", ["a_", "b_"])
-def test_test_policy_vectorized_matches_reference(golden, prefix):
+def test_test_policy_vectorized_matches_reference(golden, prefix, kernel):
     from rl_sde_is_b200.approximate_methods import estimate_fht_vectorized, test_policy_vectorized
     g = golden("rollout_numpy_1d")
     e = g[prefix + "env"]
@@ -142,22 +150,23 @@ def test_test_policy_vectorized_matches_reference(golden, prefix):
     env.discretize_state_space(float(e[4]))
     model = _model_from(g, prefix, 1)
     res = test_policy_vectorized(env, model, batch_size=g[prefix + "noise"].shape[1], policy_opt=g[prefix + "policy_opt"],
-                                 noise=g[prefix + "noise"])
+                                 noise=g[prefix + "noise"], kernel=kernel)
     want = g[prefix + "result"]
     assert res[2] == want[2]                                                     # mean hit index: exact
     np.testing.assert_allclose(res[0], want[0], rtol=1e-6)
     np.testing.assert_allclose(res[1], want[1], rtol=1e-5)
     np.testing.assert_allclose(res[3], want[3], rtol=1e-4, atol=1e-9)
-    fht = estimate_fht_vectorized(env, model, batch_size=g[prefix + "noise"].shape[1], noise=g[prefix + "noise"])
+    fht = estimate_fht_vectorized(env, model, batch_size=g[prefix + "noise"].shape[1], noise=g[prefix + "noise"], kernel=kernel)
     assert fht == float(g[prefix + "fht"])
 
 
-def test_estimate_fht_2d_matches_reference(golden):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_estimate_fht_2d_matches_reference(golden, kernel):
     from rl_sde_is_b200.approximate_methods import estimate_fht_vectorized
     g = golden("rollout_numpy_2d")
     d, alpha, beta, dt = _env(g, "a_")
     fht = estimate_fht_vectorized(_make_env(d, alpha, beta, dt), _model_from(g, "a_", d), batch_size=g["a_noise"].shape[1],
-                                  noise=g["a_noise"])
+                                  noise=g["a_noise"], kernel=kernel)
     assert fht == float(g["a_fht"])
 
 
@@ -223,10 +232,17 @@ def test_rng_rollout_equals_replay_of_its_own_noise():
         env = _make_env(d, 1.0, 1.0, 0.005)
         params = R.flat_parameters(m).detach().numpy()
         K, lim = 300, 1500
-        a = R.rollout_forward(R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(d, 32), params, K, seed=99, n_steps_lim=lim)
         noise = R.noise_fill(99, K, d, lim, 0.005)
-        b = R.rollout_forward(R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(d, 32), params, K, noise=noise, n_steps_lim=lim)
-        assert torch.equal(a.T, b.T) and torch.equal(a.G, b.G) and torch.equal(a.S, b.S)
+        outs = {}
+        for kernel in KERNELS:
+            a = R.rollout_forward(R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(d, 32), params, K, seed=99, n_steps_lim=lim, kernel=kernel)
+            b = R.rollout_forward(R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(d, 32), params, K, noise=noise, n_steps_lim=lim, kernel=kernel)
+            assert torch.equal(a.T, b.T) and torch.equal(a.G, b.G) and torch.equal(a.S, b.S)
+            outs[kernel] = a
+        # the two kernel families sum the dot products in different orders: same trajectories to rounding
+        same = outs["thread"].T == outs["warp"].T
+        assert same.float().mean() > 0.97
+        assert torch.allclose(outs["thread"].G[same], outs["warp"].G[same], rtol=2e-5)
 
 
 def test_rng_rollout_matches_c_restatement_per_trajectory():
