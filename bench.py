@@ -142,7 +142,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.01)
 
     def __enter__(self):
         if self.nv is not None:
@@ -179,6 +179,8 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
@@ -196,7 +198,7 @@ def run_gpu_arm(args):
                                 traj_offset=shard.traj_offset, K_global=shard.K_global, tanh=args.tanh, device=dev)
         stats = out.stats_dev
         if world > 1:
-            dist.all_reduce(stats)                      # the path's only exchange step: 16 doubles
+            shard.all_reduce_stats(stats)               # the path's only exchange step: 16 doubles
         return stats
 
     for w in range(args.warmup):

@@ -42,7 +42,7 @@ def _numpy_path_rollout(env, model, batch_size, k_max, policy_opt, *, noise, see
     out = R.rollout_forward(env_c, mlp_c, params_host, int(batch_size), **opts)
     stats = out.stats_dev
     if dist is not None:
-        stats = dist.all_reduce_sum(stats.clone())
+        stats = dist.all_reduce_stats(stats.clone())
     return out, stats.cpu().numpy()
 
 

@@ -41,6 +41,16 @@ class Shard:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
+    def all_reduce_stats(self, stats):
+        """Statistics record of the global batch: every entry is a sum over trajectories except the maximum."""
+        from ._lib import ST_MAX_T
+        if self.world_size > 1:
+            mx = stats[ST_MAX_T].clone()
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+            stats[ST_MAX_T] = mx
+        return stats
+
     @classmethod
     def from_env(cls, K_global, group=None):
         if dist.is_available() and dist.is_initialized():

@@ -80,7 +80,7 @@ class _LossWithAux(torch.autograd.Function):
         holder["out"] = out
         K_global = out.cfg.K_global
         if dist is not None:
-            stats = dist.all_reduce_sum(out.stats_dev.clone())
+            stats = dist.all_reduce_stats(out.stats_dev.clone())
             loss = float(stats[L.ST_SUM_LOSS].item()) / K_global
             holder["stats_global"] = stats.cpu().numpy()
         else:
