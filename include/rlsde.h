@@ -205,6 +205,21 @@ int rlsde_tables(const double* state_grid_dev, int64_t Ns, const double* action_
 int rlsde_tables_colsum(const double* P_dev, int64_t n_sprime, int64_t Ns, int64_t Na, double* colsum_dev,
                         void* stream);
 
+/*
+ * Bellman sweep over a device-resident transition tensor (the contraction inside q_table_update_vect
+ * tabular_dp_qvalue_iteration.py:35-43, v_table_update_vect tabular_dp_value_iteration.py:41-52 and policy_update_vect
+ * tabular_dp_policy_iteration.py:37-49):
+ *   values[s, a] = R[s, a] + (1 - in_ts[s]) * gamma * sum_{s'} P[s', s, a] * v[s']
+ * P_dev: double[Ns][Ns][Na] as written by rlsde_tables; v_dev: double[Ns]; values_dev: double[Ns][Na].
+ * scratch_dev: rlsde_dp_scratch_bytes(Ns, Na) bytes.  HBM-read bound: 8 Ns^2 Na bytes per sweep.
+ */
+size_t rlsde_dp_scratch_bytes(int64_t Ns, int64_t Na);
+int rlsde_dp_sweep(const double* P_dev, int64_t Ns, int64_t Na, const double* R_dev, const uint8_t* in_ts_dev,
+                   const double* v_dev, double gamma, double* values_dev, void* scratch_dev, size_t scratch_bytes,
+                   void* stream);
+/* vmax[s] = max_a values[s, a] and argmax[s] = first maximiser (np.max / np.argmax, axis 1); either output may be NULL */
+int rlsde_dp_rowmax(const double* values_dev, int64_t Ns, int64_t Na, double* vmax_dev, int64_t* argmax_dev, void* stream);
+
 /* reward_type for rlsde_env_step */
 #define RLSDE_REWARD_STATE_ACTION 0            /* done and r on the current state   environments.py:152-155 */
 #define RLSDE_REWARD_STATE_ACTION_NEXT_STATE 1 /* done on the next state            environments.py:157-160 */

@@ -227,3 +227,28 @@ def p_tensor(state_grid, action_grid, is_in_ts, alpha, beta, dt, h_state, sprime
     n_ts = int(is_in_ts.sum())
     prob[:, ts_cols, :] = np.where(is_in_ts[sp], 1.0 / n_ts, 0.0)[:, None, None]      # dynamic_programming.py:25-26
     return prob
+
+
+# --------------------------------------------------------------------------------------------------
+# DP sweeps over the tables
+# --------------------------------------------------------------------------------------------------
+def bellman_values(r_table, p_tensor, is_in_ts, v, gamma):
+    """values[s, a] = r[s, a] + (1 - d[s]) gamma sum_s' P[s', s, a] v[s']: the contraction shared by
+    q_table_update_vect (tabular_dp_qvalue_iteration.py:35-43), v_table_update_vect (tabular_dp_value_iteration.py:41-52)
+    and policy_update_vect (tabular_dp_policy_iteration.py:37-49)."""
+    live = 1 - np.where(is_in_ts, 1, 0)[:, None]
+    return r_table + live * gamma * np.einsum("psa,p->sa", p_tensor, v)
+
+
+def q_sweep(r_table, p_tensor, is_in_ts, q, gamma):
+    return bellman_values(r_table, p_tensor, is_in_ts, q.max(axis=1), gamma)
+
+
+def v_sweep(r_table, p_tensor, is_in_ts, v, gamma):
+    return bellman_values(r_table, p_tensor, is_in_ts, v, gamma).max(axis=1)
+
+
+def greedy_policy_indices(r_table, p_tensor, is_in_ts, v, gamma, null_action_idx):
+    idx = np.argmax(bellman_values(r_table, p_tensor, is_in_ts, v, gamma), axis=1)
+    idx[is_in_ts] = null_action_idx
+    return idx

@@ -37,6 +37,7 @@ EXPORTED_SYMBOLS = [
     "rlsde_version", "rlsde_strerror", "rlsde_last_cuda_error", "rlsde_device_info", "rlsde_supported",
     "rlsde_param_count", "rlsde_workspace_bytes", "rlsde_rollout_fwd", "rlsde_rollout_bwd", "rlsde_reduce_stats",
     "rlsde_tables", "rlsde_tables_colsum", "rlsde_env_step", "rlsde_noise_fill",
+    "rlsde_dp_scratch_bytes", "rlsde_dp_sweep", "rlsde_dp_rowmax",
 ]
 
 
@@ -99,8 +100,12 @@ def load():
     lib.rlsde_tables_colsum.argtypes = [vp, i64, i64, i64, vp, vp]
     lib.rlsde_env_step.argtypes = [C.POINTER(RlsdeEnv), i64, vp, vp, vp, u64, i64, i64, u32, i32, vp, vp, vp, vp, vp]
     lib.rlsde_noise_fill.argtypes = [u64, i64, i64, i32, i64, i64, dbl, vp, vp]
+    lib.rlsde_dp_scratch_bytes.restype = C.c_size_t
+    lib.rlsde_dp_scratch_bytes.argtypes = [i64, i64]
+    lib.rlsde_dp_sweep.argtypes = [vp, i64, i64, vp, vp, vp, dbl, vp, vp, C.c_size_t, vp]
+    lib.rlsde_dp_rowmax.argtypes = [vp, i64, i64, vp, vp, vp]
     for name in ("rlsde_device_info", "rlsde_supported", "rlsde_rollout_fwd", "rlsde_rollout_bwd", "rlsde_reduce_stats",
-                 "rlsde_tables", "rlsde_tables_colsum", "rlsde_env_step", "rlsde_noise_fill"):
+                 "rlsde_tables", "rlsde_tables_colsum", "rlsde_env_step", "rlsde_noise_fill", "rlsde_dp_sweep", "rlsde_dp_rowmax"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

@@ -38,4 +38,9 @@ int launch_tables(const double* state_grid, long long Ns, const double* action_g
 int launch_tables_colsum(const double* P, long long n_sprime, long long Ns, long long Na, double* colsum,
                          cudaStream_t stream);
 
+int launch_dp_sweep(const double* P, long long Ns, long long Na, const double* R, const unsigned char* in_ts,
+                    const double* v, double gamma, double* values, double* scratch, cudaStream_t stream);
+size_t dp_sweep_scratch_bytes(long long Ns, long long Na);
+int launch_dp_rowmax(const double* values, long long Ns, long long Na, double* vmax, long long* arg, cudaStream_t stream);
+
 }  // namespace rlsde

@@ -268,6 +268,25 @@ int rlsde_tables_colsum(const double* P_dev, int64_t n_sprime, int64_t Ns, int64
   return RLSDE_OK;
 }
 
+size_t rlsde_dp_scratch_bytes(int64_t Ns, int64_t Na) { return (Ns > 0 && Na > 0) ? dp_sweep_scratch_bytes(Ns, Na) : 0; }
+
+int rlsde_dp_sweep(const double* P_dev, int64_t Ns, int64_t Na, const double* R_dev, const uint8_t* in_ts_dev,
+                   const double* v_dev, double gamma, double* values_dev, void* scratch_dev, size_t scratch_bytes,
+                   void* stream_) {
+  if (!P_dev || !R_dev || !in_ts_dev || !v_dev || !values_dev || !scratch_dev || Ns < 1 || Na < 1) return RLSDE_ERR_INVALID_ARG;
+  if (scratch_bytes < dp_sweep_scratch_bytes(Ns, Na)) return RLSDE_ERR_WORKSPACE;
+  const int lrc = launch_dp_sweep(P_dev, Ns, Na, R_dev, in_ts_dev, v_dev, gamma, values_dev, (double*)scratch_dev, (cudaStream_t)stream_);
+  if (lrc != 0) return cuda_fail((cudaError_t)lrc, "dp_sweep launch");
+  return RLSDE_OK;
+}
+
+int rlsde_dp_rowmax(const double* values_dev, int64_t Ns, int64_t Na, double* vmax_dev, int64_t* argmax_dev, void* stream_) {
+  if (!values_dev || Ns < 1 || Na < 1 || (!vmax_dev && !argmax_dev)) return RLSDE_ERR_INVALID_ARG;
+  const int lrc = launch_dp_rowmax(values_dev, Ns, Na, vmax_dev, (long long*)argmax_dev, (cudaStream_t)stream_);
+  if (lrc != 0) return cuda_fail((cudaError_t)lrc, "dp_rowmax launch");
+  return RLSDE_OK;
+}
+
 int rlsde_env_step(const rlsde_env* env, int64_t K, const void* state_dev, const float* action_dev,
                    const float* dbt_in_dev, uint64_t seed, int64_t traj_offset, int64_t pass_index, uint32_t flags,
                    int32_t reward_type, void* next_state_dev, void* reward_dev, uint8_t* done_dev, float* dbt_out_dev,

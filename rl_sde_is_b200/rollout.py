@@ -177,7 +177,10 @@ def rollout_backward(env_c, mlp_c, params_host, fwd: RolloutOut, loss_scale, *, 
     ws = _workspace(dev)
     with torch.cuda.device(dev):
         # longest trajectories first (stable sort => deterministic): balances the lock-step lanes of the reverse pass
-        order = torch.argsort(fwd.T, descending=True, stable=True) if balance and fwd.T.numel() > 32 else None
+        # (the warp-per-trajectory kernels, used for small batches, take trajectories in index order)
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        thread_path = (fwd.cfg.flags & L.F_KERNEL_THREAD) or not ((fwd.cfg.flags & L.F_KERNEL_WARP) or fwd.T.numel() <= 16 * n_sm)
+        order = torch.argsort(fwd.T, descending=True, stable=True) if balance and thread_path and fwd.T.numel() > 32 else None
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = lib.rlsde_rollout_bwd(env_c, mlp_c, params_host.ctypes.data, fwd.cfg, _ptr(noise), _ptr(fwd.G), _ptr(fwd.T),
                                    _ptr(fwd.path), _ptr(order), float(loss_scale), _ptr(grad), _ptr(ws), ws.numel(), stream)

@@ -24,6 +24,8 @@ Fixtures (all arrays little-endian, names are the keys of the .npz):
   env_step.npz           single ``env.step`` / ``env.step_torch`` calls, both reward types.
   reinforce_iters.npz    three ``zero_grad -> loss -> backward -> Adam.step`` iterations
                          (reinforce_deterministic_core.py:234-243) with recorded noise.
+  dp_sweeps.npz          ``q_table_update_vect`` / ``v_table_update_vect`` / ``policy_update_vect`` on the h = 0.1 tables
+                         (tabular_dp_{qvalue,value,policy}_iteration.py), 3 sweeps at gamma = 1 and 0.97, and 200 sweeps.
   tables.npz             ``compute_r_table`` / ``compute_p_tensor_batch`` (dynamic_programming.py:3-36):
                          full tensors at h=0.1, strided sub-sample + checksums at h=0.01, and a
                          (alpha, beta) = (1, 4) case.
@@ -129,10 +131,46 @@ def numpy_rollout_case(am, env, model, K, seed, policy_opt, out, prefix):
     out[prefix + "fht"] = np.array(fht, dtype=np.float64)
 
 
+def dp_sweeps(env1, dp):
+    """dp_sweeps.npz: reference Bellman sweeps over the h = 0.1 tables (tabular_dp_qvalue_iteration.py:35-43,
+    tabular_dp_value_iteration.py:41-52, tabular_dp_policy_iteration.py:37-49) -- SURVEY 8f-1."""
+    import rl_sde_is.tabular_dp_policy_iteration as pit
+    import rl_sde_is.tabular_dp_qvalue_iteration as qit
+    import rl_sde_is.tabular_dp_value_iteration as vit
+    out = {}
+    env = env1.DoubleWellStoppingTime1D(beta=1.0, alpha=1.0, dt=0.005)
+    env.set_action_space_bounds()
+    env.discretize_state_space(0.1)
+    env.discretize_action_space(0.1)
+    R = dp.compute_r_table(env)
+    P = dp.compute_p_tensor_batch(env)
+    rng = np.random.default_rng(42)
+    q0 = -rng.random((env.n_states, env.n_actions))
+    v0 = -rng.random(env.n_states)
+    out["q0"], out["v0"], out["gamma"] = q0, v0, np.array([1.0, 0.97])
+    for gi, gamma in enumerate((1.0, 0.97)):
+        q = q0.copy()
+        for it in range(3):
+            q = qit.q_table_update_vect(env, R, P, q, gamma)
+            out[f"g{gi}_q{it + 1}"] = q
+        out[f"g{gi}_v1"] = vit.v_table_update_vect(env, R, P, v0, gamma)
+        out[f"g{gi}_pi1"] = pit.policy_update_vect(env, R, P, v0, gamma)
+    q = q0.copy()
+    for it in range(200):
+        q = qit.q_table_update_vect(env, R, P, q, 1.0)
+    out["q200"] = q
+    out["null_action_idx"] = np.array(env.null_action_idx)
+    np.savez_compressed(os.path.join(OUT_DIR, "dp_sweeps.npz"), **out)
+    print("  dp_sweeps: V(s_init) after 200 sweeps =", np.max(q[env.state_init_idx]))
+
+
 def main():
     t_start = time.time()
     env1, env2, core, am, dp, tdt = import_reference()
     torch.set_num_threads(1)
+    if len(sys.argv) > 1 and sys.argv[1] == "dp":      # regenerate only the DP-sweep fixture
+        dp_sweeps(env1, dp)
+        return
 
     # ---------------------------------------------------------------- torch path, 1-D
     out = {}
@@ -280,6 +318,8 @@ def main():
     out["a_env"] = np.array([env.d, 1.0, env.beta, env.dt], dtype=np.float64)
     print(f"  numpy 2d fht={fht} passes={len(rec.noise)}")
     np.savez_compressed(os.path.join(OUT_DIR, "rollout_numpy_2d.npz"), **out)
+
+    dp_sweeps(env1, dp)
 
     for f in sorted(os.listdir(OUT_DIR)):
         if f.endswith(".npz"):

@@ -144,3 +144,15 @@ def test_c_tables_match_reference(golden):
     P, R = c_oracle.tables(g["h01_state_grid"], g["h01_action_grid"], g["h01_is_in_ts"], alpha, beta, dt, hs)
     np.testing.assert_allclose(P, g["h01_P"], rtol=0, atol=1e-15)   # glibc erf/erfc vs cephes ndtr
     assert np.array_equal(R, g["h01_R"])
+
+
+def test_dp_sweeps_match_reference(golden):
+    g, t = golden("dp_sweeps"), golden("tables")
+    R, P, ts = t["h01_R"], t["h01_P"], t["h01_is_in_ts"]
+    for gi, gamma in enumerate(g["gamma"]):
+        q = g["q0"].copy()
+        for it in range(3):
+            q = ref.q_sweep(R, P, ts, q, gamma)
+            np.testing.assert_allclose(q, g[f"g{gi}_q{it + 1}"], rtol=0, atol=1e-13)      # BLAS vs einsum summation order
+        np.testing.assert_allclose(ref.v_sweep(R, P, ts, g["v0"], gamma), g[f"g{gi}_v1"], rtol=0, atol=1e-13)
+        assert np.array_equal(ref.greedy_policy_indices(R, P, ts, g["v0"], gamma, int(g["null_action_idx"][0])), g[f"g{gi}_pi1"])
