@@ -198,34 +198,6 @@ def choose_ckpt_every(K, d, n_steps_lim, budget_bytes=8 << 30):
         "pass a smaller n_steps_lim")
 
 
-class RolloutLoss(torch.autograd.Function):
-    """eff_loss = mean_k(-G_k - sg(G_k) S_k) as a differentiable function of the flat policy parameters.
-
-    forward launches K1 (with state checkpoints), backward launches K2; what autograd does in the
-    reference over ~25 nodes per pass (reinforce_deterministic_core.py:52-93, :240).
-    """
-
-    @staticmethod
-    def forward(ctx, flat_params, env_c, mlp_c, K, opts):
-        params_host = flat_params.detach().to("cpu", torch.float32).contiguous().numpy()
-        out = rollout_forward(env_c, mlp_c, params_host, K, store_path=True, want_logw=False, **opts)
-        st = out.stats                        # synchronises: the loss value is needed on the host anyway
-        K_global = out.cfg.K_global
-        loss = st[L.ST_SUM_LOSS] / K_global
-        ctx.env_c, ctx.mlp_c, ctx.params_host, ctx.out = env_c, mlp_c, params_host, out
-        ctx.noise = opts.get("noise")
-        ctx.device = opts.get("device")
-        ctx.K_global = K_global
-        return torch.tensor(loss, dtype=torch.float32, device=flat_params.device)
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        g = rollout_backward(ctx.env_c, ctx.mlp_c, ctx.params_host, ctx.out, 1.0 / ctx.K_global, noise=ctx.noise,
-                             device=ctx.device)
-        g = g.to(grad_out.device) * grad_out.to(torch.float32)
-        return g, None, None, None, None
-
-
 def noise_fill(seed, K, d, n_pass, dt, *, traj_offset=0, pass_begin=0, device=None):
     """Increments dB[pass, k, i] exactly as the rollout kernels generate them in-kernel."""
     lib = L.load()
