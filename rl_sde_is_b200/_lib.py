@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "librlsde_b200.so")
+LIB_PATH = os.environ.get("RLSDE_LIB_PATH") or os.path.join(_PKG_DIR, "librlsde_b200.so")
 
 RLSDE_MAX_D = 16
 RLSDE_NSTATS = 16

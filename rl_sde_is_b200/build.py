@@ -18,15 +18,18 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
-OBJ_DIR = os.path.join(ROOT, "build", "obj")
-LIB_PATH = os.path.join(PKG_DIR, "librlsde_b200.so")
+# A/B variants for kernel experiments: RLSDE_VARIANT=name RLSDE_NVCC_EXTRA="-DFOO=1" builds librlsde_b200_name.so
+# from its own object directory; select it at run time with RLSDE_LIB_PATH.
+VARIANT = os.environ.get("RLSDE_VARIANT", "")
+OBJ_DIR = os.path.join(ROOT, "build", "obj" + ("_" + VARIANT if VARIANT else ""))
+LIB_PATH = os.path.join(PKG_DIR, "librlsde_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "librlsde_oracle.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("RLSDE_NVCC_EXTRA", "").split()
 # ptxas' default register-usage heuristic (level >= 4) degenerates on the fully unrolled reverse-pass
 # kernels (32 registers + everything spilled to local memory); level 3 allocates normally.
 EXTRA_FLAGS = {"bwd_": ["-Xptxas", "-regUsageLevel=3"]}

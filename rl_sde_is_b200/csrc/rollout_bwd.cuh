@@ -53,8 +53,19 @@ inline size_t bwd_workspace_bytes() { return (size_t)BWD_MAX_WARPS * BWD_MAX_PAR
 
 // XOR swizzle of a [32 lanes][H] float tile at float4 granularity: a lane writing its own row with
 // STS.128, a broadcast read of one row, and a read of one column element per lane are all conflict-free.
+#ifndef RLSDE_BWD_PAD
+#define RLSDE_BWD_PAD 0      // 1: rows padded to H + 4 floats instead of the XOR swizzle (fewer instructions, measured slower)
+#endif
 template <int H>
-__device__ __forceinline__ int swz(int row, int col) { return row * H + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3)); }
+__device__ __forceinline__ int swz(int row, int col) {
+#if RLSDE_BWD_PAD
+  return row * (H + 4) + col;
+#else
+  return row * H + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3));
+#endif
+}
+template <int H>
+__host__ __device__ constexpr int tile_floats() { return 32 * (H + (RLSDE_BWD_PAD ? 4 : 0)); }
 
 template <int H>
 __device__ __forceinline__ void stage_row(float* tile, int lane, const float (&v)[H]) {
@@ -130,9 +141,9 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MIN_BLOCKS) rollout_bwd_kernel(
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
-  float* tileH1 = smem + (size_t)warp_in_block * (2 * 32 * H + 64 * D);  // first-layer activations [32][H]
-  float* tileB = tileH1 + 32 * H;                                        // h2, then dz2, then dz1  [32][H]
-  float* vecA = tileB + 32 * H;                                          // a or x                  [32][D]
+  float* tileH1 = smem + (size_t)warp_in_block * (2 * tile_floats<H>() + 64 * D);  // first-layer activations [32][H]
+  float* tileB = tileH1 + tile_floats<H>();                                        // h2, then dz2, then dz1  [32][H]
+  float* vecA = tileB + tile_floats<H>();                                          // a or x                  [32][D]
   const bool inject = (A.flags & RLSDE_F_NOISE_INJECTED) != 0;
   const bool s_exact = (A.flags & RLSDE_F_STOCH_INT_EXACT) != 0;
   const int C = A.ckpt_every;

@@ -11,6 +11,9 @@ What runs where:
     through ``rlsde_env_step`` -- API completeness only; the fast path is the whole-rollout kernel.
   * grids, index sets, action bounds (environments.py:250-360): NumPy on the host, called once
     ("stay in Python/NumPy; pass resulting arrays to the kernels").
+  * ``step_vectorized_stopped`` (environments.py:164-199) is not provided: it has no caller in the reference and
+    raises a broadcasting ValueError there (``f(states[idx])`` has shape (n,) against (n, 1) action terms), so there
+    is no behaviour to reproduce.
   * ``DoubleWellStoppingTimeND`` generalises the 2-D class to any d <= 16 (the d = 10 config has no
     reference environment; semantics follow environments_2d.py:15,50-61,114-121,184-205).
 """

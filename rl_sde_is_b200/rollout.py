@@ -56,7 +56,8 @@ _workspaces = {}
 
 
 def _workspace(device):
-    key = (device.type, device.index)
+    # one scratch buffer per (device, stream): the work counters inside must not be shared by concurrent launches
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None:
         n = L.load().rlsde_workspace_bytes(0)

@@ -137,6 +137,10 @@ def _gloo_worker(rank, world, port, K_global, q):
     stats[L.ST_SUM_G] = ids.sum()
     buf = sh.all_reduce_sum(D.pack_grad_and_stats(grad, stats))
     g, s = D.unpack_grad_and_stats(buf, 3)
+    rec = stats.clone()
+    rec[L.ST_MAX_T] = 100.0 + rank                  # the maximum entry must be max-reduced, everything else summed
+    rec = sh.all_reduce_stats(rec)
+    assert float(rec[L.ST_MAX_T]) == 100.0 + world - 1 and float(rec[L.ST_N]) == K_global
     q.put((rank, sh.traj_offset, sh.K_local, g.tolist(), float(s[L.ST_N]), float(s[L.ST_SUM_G])))
     dist.destroy_process_group()
 
