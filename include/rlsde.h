@@ -165,6 +165,27 @@ int rlsde_rollout_fwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
                       void* stream);
 
 /*
+ * Forward rollout that also streams every transition out (replay-buffer sampler):
+ * sample_trajectories_buffer_vectorized approximate_methods.py:513-545 + ReplayBuffer.store_vectorized
+ * replay_buffers.py:56-68.  For trajectory t and each pass k it executes (k = 0 .. k*, the detecting pass included;
+ * k = 0 .. n_steps_lim-1 if never detected) the tuple lands at slot  slot_base_dev[t] + k :
+ *   states[slot][d]  = X_k            actions[slot][d] = policy(X_k)
+ *   rewards[slot]    = -(1 + |u|^2/2) dt, or -0 on the detecting pass (environments.py:104-110, 152-155)
+ *   next_states[slot][d] = X_{k+1} (the Euler-Maruyama pass is evaluated on the detecting pass too, as env.step does)
+ *   done[slot]       = X_k in the target set
+ * all cast to float32 / uint8 the way the reference's float32 buffer arrays cast them.  The number of passes of a
+ * trajectory is only known after a rollout: call rlsde_rollout_fwd first with the same cfg (the counter-based noise
+ * makes the second rollout identical), build slot_base as the exclusive prefix sum of (T >= 0 ? T + 1 : n_steps_lim),
+ * then call this.  Slots are trajectory-major; the reference's pass-major order is a stable sort by k.
+ * G/S/T/stats as in rlsde_rollout_fwd.  RLSDE_F_STORE_PATH is not accepted.
+ */
+int rlsde_rollout_transitions(const rlsde_env* env, const rlsde_mlp* mlp, const float* params_host,
+                              const rlsde_rollout_cfg* cfg, const float* noise_dev, const int64_t* slot_base_dev,
+                              float* states_dev, float* actions_dev, float* rewards_dev, float* next_states_dev,
+                              uint8_t* done_dev, void* G_dev, void* S_dev, int32_t* T_dev, double* stats_dev,
+                              void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/*
  * Reverse (adjoint) pass: gradient of  L = loss_scale * sum_k ( -G_k - sg(G_k) S_k )  w.r.t. the
  * policy parameters, through the whole rollout (what eff_loss.backward() computes,
  * reinforce_deterministic_core.py:91,240; recursion in SURVEY App. C).  Needs the G/T outputs

@@ -152,6 +152,41 @@ def rollout_stats_numpy(d, alpha, beta, dt, params, noise, policy_opt=None, h_st
     return dict(ep_rets=ep_rets, ep_lens=ep_lens, l2=l2_fht if policy_opt is not None else None, all_hit=bool(seen.all()))
 
 
+def transitions_numpy(d, alpha, beta, dt, params, noise, n_max, lb=1.0, rb=2.0, x0=-1.0):
+    """Replay of ``sample_trajectories_buffer_vectorized`` (approximate_methods.py:513-545) on recorded increments:
+    what ``ReplayBuffer.store_vectorized`` (replay_buffers.py:56-68) has received when the sampler returns.
+
+    Every pass stores the tuples of the episodes whose hit had not been detected BEFORE that pass (the detecting pass
+    itself is stored, with done = True and reward -0), in episode order; the float64 next state / reward of the NumPy
+    step are cast to the buffer's float32 arrays on assignment.  Returns dict(states, actions, rewards, next_states, done).
+    """
+    noise = np.asarray(noise, dtype=np.float32)
+    K = noise.shape[1]
+    sigma = np.sqrt(2.0 / beta)
+    alpha_v = alpha if d == 1 else np.full(d, alpha)
+    states = np.full((K, d), np.float32(x0))
+    seen = np.zeros(K, dtype=bool)
+    cols = {k: [] for k in ("states", "actions", "rewards", "next_states", "done")}
+    for k in range(min(int(n_max), noise.shape[0])):
+        with torch.no_grad():
+            actions = policy_torch(params, torch.FloatTensor(states)).numpy()
+        nxt = states + (-(4 * alpha_v * states * (states ** 2 - 1)) + sigma * actions) * dt + sigma * noise[k]
+        done = ((states[:, 0] >= lb) & (states[:, 0] <= rb)) if d == 1 else (states >= lb).all(axis=1)
+        running = -(np.ones(K) + 0.5 * np.linalg.norm(actions, axis=1) ** 2) * dt
+        r = np.where(done, -np.zeros(K), running)
+        live = ~seen
+        cols["states"].append(states[live].astype(np.float32))
+        cols["actions"].append(actions[live].astype(np.float32))
+        cols["rewards"].append(r[live].astype(np.float32))
+        cols["next_states"].append(nxt[live].astype(np.float32))
+        cols["done"].append(done[live])
+        seen |= done
+        if seen.all():
+            break
+        states = nxt
+    return {k: np.concatenate(v, axis=0) for k, v in cols.items()}
+
+
 def test_policy_result(stats, with_l2):
     """The reference's return tuple (approximate_methods.py:640-648) from ``rollout_stats_numpy`` output."""
     if not stats["all_hit"]:

@@ -6,6 +6,9 @@ Reference: rl_sde_is/approximate_methods.py
 Both follow the NumPy path of the reference: float64 state and accumulators with a float32 policy
 (SURVEY App. A-5), hit rule ``lb <= x <= rb`` in 1-D (:48-49), hit index ``ep_lens = k*`` (0-based).
 
+``sample_trajectories_buffer_vectorized(env, model, replay_buffer, batch_size, n_max)`` (:513-545) is the TD3 data
+path: the same rollout with a transition-stream epilogue, stored through ``store_vectorized``.
+
 ``is_estimate`` is build-side: the importance-sampling estimator of
 Psi(x0) = E[exp(-tau)] from the same rollout, mean and relative error.
 """
@@ -89,3 +92,39 @@ def is_estimate(env, model, batch_size, n_steps_lim=10**7, *, noise=None, seed=N
     _, st = _numpy_path_rollout(env, model, batch_size, n_steps_lim, None, noise=noise, seed=seed, tanh=tanh, kernel=kernel,
                                 state_f64=state_f64, device=device, dist=dist, stoch_int="exact", want_logw=True)
     return R.summarize(st)
+
+
+def sample_transitions(env, model, batch_size, n_max, *, noise=None, seed=None, tanh="precise", state_f64=True,
+                       order="reference", device=None):
+    """Device-resident ``rollout.Transitions`` of ``batch_size`` episodes under the policy (NumPy-path arithmetic)."""
+    d, H = R.policy_shape(model)
+    if d != env.d:
+        raise L.RlsdeError(f"policy dimension {d} != env.d {env.d}")
+    rule = L.HIT_X0_IN_LB_RB if env.d == 1 else L.HIT_ALL_GE_LB
+    env_c = R.env_struct(env, rule)
+    mlp_c = L.make_mlp(d, H)
+    dev = R._cuda_device(device)
+    params_host = R.flat_parameters(model).detach().to("cpu", torch.float32).contiguous().numpy()
+    if noise is not None:
+        noise = torch.as_tensor(np.ascontiguousarray(noise, dtype=np.float32)) if not torch.is_tensor(noise) else noise
+        noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+    return R.rollout_transitions(env_c, mlp_c, params_host, int(batch_size), seed=_next_seed(seed), n_max=int(n_max),
+                                 noise=noise, tanh=tanh, state_f64=state_f64, order=order, device=dev)
+
+
+def sample_trajectories_buffer_vectorized(env, model, replay_buffer, batch_size, n_max, *, noise=None, seed=None,
+                                          tanh="precise", state_f64=True, device=None):
+    """Roll ``batch_size`` episodes out (at most ``n_max`` passes each) and append every transition to ``replay_buffer``
+    through its ``store_vectorized`` -- one call with the tuples in the reference's pass-major order (:513-545).
+
+    ``replay_buffer`` is a host ``ReplayBuffer`` (NumPy arrays, like the reference's) or a ``DeviceReplayBuffer``
+    (the tuples then never leave the GPU).  Returns the number of transitions stored."""
+    from .replay_buffers import DeviceReplayBuffer
+    tr = sample_transitions(env, model, batch_size, n_max, noise=noise, seed=seed, tanh=tanh, state_f64=state_f64,
+                            order="reference", device=device)
+    if isinstance(replay_buffer, DeviceReplayBuffer):
+        replay_buffer.store_vectorized(tr.states, tr.actions, tr.rewards, tr.next_states, tr.done)
+    else:
+        replay_buffer.store_vectorized(tr.states.cpu().numpy(), tr.actions.cpu().numpy(), tr.rewards.cpu().numpy(),
+                                       tr.next_states.cpu().numpy(), tr.done.cpu().numpy())
+    return len(tr)

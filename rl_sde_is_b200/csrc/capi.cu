@@ -149,10 +149,21 @@ size_t rlsde_workspace_bytes(int64_t K) {
   return WS_COUNTER_BYTES + WS_STATS_BYTES + WS_CONT_BYTES + bwd_workspace_bytes();
 }
 
-int rlsde_rollout_fwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* params_host,
-                      const rlsde_rollout_cfg* cfg, const float* noise_dev, const float* policy_opt_dev,
-                      void* G_dev, void* S_dev, int32_t* T_dev, void* l2_dev, void* logw_dev, float* path_dev,
-                      double* stats_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
+// transition-stream outputs of a forward rollout (all null = none)
+struct TransitionOut {
+  const long long* base;
+  float* state;
+  float* action;
+  float* reward;
+  float* next_state;
+  unsigned char* done;
+};
+
+static int rollout_fwd_impl(const rlsde_env* env, const rlsde_mlp* mlp, const float* params_host,
+                            const rlsde_rollout_cfg* cfg, const float* noise_dev, const float* policy_opt_dev,
+                            void* G_dev, void* S_dev, int32_t* T_dev, void* l2_dev, void* logw_dev, float* path_dev,
+                            double* stats_dev, const TransitionOut& tr, void* workspace_dev, size_t workspace_bytes,
+                            void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = check_env_mlp(env, mlp);
   if (rc != RLSDE_OK) return rc;
@@ -167,6 +178,9 @@ int rlsde_rollout_fwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
   if (policy_opt_dev && (cfg->n_grid < 1 || !(cfg->grid_h > 0) || env->d != 1)) return RLSDE_ERR_INVALID_ARG;
   A.noise = noise_dev; A.policy_opt = policy_opt_dev;
   A.G = G_dev; A.S = S_dev; A.T = T_dev; A.l2 = l2_dev; A.logw = logw_dev; A.path = path_dev;
+  A.tr_base = tr.base; A.tr_state = tr.state; A.tr_action = tr.action; A.tr_reward = tr.reward;
+  A.tr_next = tr.next_state; A.tr_done = tr.done;
+  if (tr.base) A.flags = (A.flags & ~RLSDE_F_KERNEL_WARP) | RLSDE_F_KERNEL_THREAD;   // the stream lives in the throughput kernel
   A.counter = (unsigned long long*)workspace_dev;
   A.ws_work_counters = (unsigned long long*)workspace_dev;
   A.ws_cont_counts = (unsigned*)((char*)workspace_dev + 256);
@@ -196,6 +210,27 @@ int rlsde_rollout_fwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
     if (lrc != 0) return cuda_fail((cudaError_t)lrc, "reduce_stats launch");
   }
   return RLSDE_OK;
+}
+
+int rlsde_rollout_fwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* params_host,
+                      const rlsde_rollout_cfg* cfg, const float* noise_dev, const float* policy_opt_dev,
+                      void* G_dev, void* S_dev, int32_t* T_dev, void* l2_dev, void* logw_dev, float* path_dev,
+                      double* stats_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  const TransitionOut none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  return rollout_fwd_impl(env, mlp, params_host, cfg, noise_dev, policy_opt_dev, G_dev, S_dev, T_dev, l2_dev, logw_dev,
+                          path_dev, stats_dev, none, workspace_dev, workspace_bytes, stream_);
+}
+
+int rlsde_rollout_transitions(const rlsde_env* env, const rlsde_mlp* mlp, const float* params_host,
+                              const rlsde_rollout_cfg* cfg, const float* noise_dev, const int64_t* slot_base_dev,
+                              float* states_dev, float* actions_dev, float* rewards_dev, float* next_states_dev,
+                              uint8_t* done_dev, void* G_dev, void* S_dev, int32_t* T_dev, double* stats_dev,
+                              void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  if (!slot_base_dev || !states_dev || !actions_dev || !rewards_dev || !next_states_dev || !done_dev) return RLSDE_ERR_INVALID_ARG;
+  if (cfg && (cfg->flags & RLSDE_F_STORE_PATH)) return RLSDE_ERR_INVALID_ARG;
+  const TransitionOut tr = {(const long long*)slot_base_dev, states_dev, actions_dev, rewards_dev, next_states_dev, done_dev};
+  return rollout_fwd_impl(env, mlp, params_host, cfg, noise_dev, nullptr, G_dev, S_dev, T_dev, nullptr, nullptr, nullptr,
+                          stats_dev, tr, workspace_dev, workspace_bytes, stream_);
 }
 
 int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* params_host,

@@ -56,6 +56,14 @@ struct FwdArgs {
   float* path;
   unsigned long long* counter;   // work counter of THIS launch (zeroed by the host wrapper)
   const long long* order;        // reverse pass: processing order of the trajectories (or nullptr = identity)
+  // ---- transition stream (replay-buffer sampler, approximate_methods.py:513-545): trajectory `t` writes the tuple of
+  //      its pass k at slot tr_base[t] + k of the five arrays below.  nullptr = no stream.
+  const long long* tr_base;
+  float* tr_state;               // [n][d]  state the pass starts from
+  float* tr_action;              // [n][d]
+  float* tr_reward;              // [n]
+  float* tr_next;                // [n][d]  state after the pass (also computed on the pass that detects the hit)
+  unsigned char* tr_done;        // [n]
   // ---- resumable rollouts (tail compaction, see rollout_fwd_inst.cuh).  A launch draws work items from
   //      [continuation records | fresh trajectories]; when its step budget ends, live lanes dump a record.
   const unsigned char* cont_in;        // records to resume, or nullptr
@@ -263,6 +271,57 @@ __global__ void __launch_bounds__(128) rollout_fwd_kernel(const __grid_constant_
         }
         --ck;
       }
+      // running cost  r = -(1 + 0.5 |u|^2) dt   (environments.py:104-110,121-127; f = 1, g = 0)
+      real r;
+      {
+        const float nn = (D == 1) ? n2 : __fmul_rn(sqrtf(n2), sqrtf(n2));
+        if (F64) {
+          // numpy: f (float64 ones) + float32(0.5 * norm(a)^2)  -> float64, times python-float dt
+          r = (real)(-__dmul_rn(__dadd_rn(1.0, (double)__fmul_rn(0.5f, nn)), A.dt_d));
+        } else {
+          r = (real)(-__fmul_rn(__fadd_rn(1.0f, __fmul_rn(0.5f, nn)), A.dt_f));
+        }
+      }
+      // Euler-Maruyama:  x + (-gradV(x) + sigma u) dt + sigma dB,  gradV = 4 alpha x (x^2 - 1)
+      real xn[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        if (F64) {
+          const double xi = (double)x[i];
+          double g;
+          if (D == 1 && k == 0) {
+            // numpy 1-D: the first pass sees a float32 state and a python-float alpha -> float32 gradient
+            const float xs = (float)xi;
+            g = (double)__fmul_rn(__fmul_rn(A.c4a_f[i], xs), __fsub_rn(__fmul_rn(xs, xs), 1.0f));
+          } else if (k == 0) {
+            // numpy d-D: float64 alpha array, but state**2 - 1 is still float32 on the first pass
+            const float xs = (float)xi;
+            g = __dmul_rn(__dmul_rn(A.c4a_d[i], xi), (double)__fsub_rn(__fmul_rn(xs, xs), 1.0f));
+          } else {
+            g = __dmul_rn(__dmul_rn(A.c4a_d[i], xi), __dsub_rn(__dmul_rn(xi, xi), 1.0));
+          }
+          const double drift = __dmul_rn(__dadd_rn(-g, __dmul_rn(A.sigma_d, (double)u[i])), A.dt_d);
+          xn[i] = (real)__dadd_rn(__dadd_rn(xi, drift), __dmul_rn(A.sigma_d, (double)dB[i]));
+        } else {
+          const float xi = (float)x[i];
+          const float g = __fmul_rn(__fmul_rn(A.c4a_f[i], xi), __fsub_rn(__fmul_rn(xi, xi), 1.0f));
+          const float drift = __fmul_rn(__fadd_rn(-g, __fmul_rn(A.sigma_f, u[i])), A.dt_f);
+          xn[i] = (real)__fadd_rn(__fadd_rn(xi, drift), __fmul_rn(A.sigma_f, dB[i]));
+        }
+      }
+      if (A.tr_base != nullptr) {
+        // (state, action, reward, next_state, done) of this pass, cast to the replay buffer's float32 arrays
+        // (replay_buffers.py:23-33,56-68); on the detecting pass the reward is -g(x) = -0 (environments.py:104-110)
+        const long long slot = A.tr_base[traj] + k;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          A.tr_state[slot * D + i] = (float)x[i];
+          A.tr_action[slot * D + i] = u[i];
+          A.tr_next[slot * D + i] = (float)xn[i];
+        }
+        A.tr_reward[slot] = hit ? -0.0f : (float)r;
+        A.tr_done[slot] = hit ? 1 : 0;
+      }
       if (hit) {
         const real Sout = s_exact ? S_prev : S;
         if (F64) {
@@ -279,43 +338,9 @@ __global__ void __launch_bounds__(128) rollout_fwd_kernel(const __grid_constant_
         A.T[traj] = k;
         alive = false;
       } else {
-        // running cost  r = -(1 + 0.5 |u|^2) dt   (environments.py:104-110,121-127; f = 1, g = 0)
-        if (F64) {
-          // numpy: f (float64 ones) + float32(0.5 * norm(a)^2)  -> float64, times python-float dt
-          const float nn = (D == 1) ? n2 : __fmul_rn(sqrtf(n2), sqrtf(n2));
-          const double r = -__dmul_rn(__dadd_rn(1.0, (double)__fmul_rn(0.5f, nn)), A.dt_d);
-          G = (real)__dadd_rn((double)G, r);
-        } else {
-          const float nn = (D == 1) ? n2 : __fmul_rn(sqrtf(n2), sqrtf(n2));
-          const float r = -__fmul_rn(__fadd_rn(1.0f, __fmul_rn(0.5f, nn)), A.dt_f);
-          G = (real)__fadd_rn((float)G, r);
-        }
-        // Euler-Maruyama:  x + (-gradV(x) + sigma u) dt + sigma dB,  gradV = 4 alpha x (x^2 - 1)
+        G = add_rn(G, r);
 #pragma unroll
-        for (int i = 0; i < D; ++i) {
-          if (F64) {
-            const double xi = (double)x[i];
-            double g;
-            if (D == 1 && k == 0) {
-              // numpy 1-D: the first pass sees a float32 state and a python-float alpha -> float32 gradient
-              const float xs = (float)xi;
-              g = (double)__fmul_rn(__fmul_rn(A.c4a_f[i], xs), __fsub_rn(__fmul_rn(xs, xs), 1.0f));
-            } else if (k == 0) {
-              // numpy d-D: float64 alpha array, but state**2 - 1 is still float32 on the first pass
-              const float xs = (float)xi;
-              g = __dmul_rn(__dmul_rn(A.c4a_d[i], xi), (double)__fsub_rn(__fmul_rn(xs, xs), 1.0f));
-            } else {
-              g = __dmul_rn(__dmul_rn(A.c4a_d[i], xi), __dsub_rn(__dmul_rn(xi, xi), 1.0));
-            }
-            const double drift = __dmul_rn(__dadd_rn(-g, __dmul_rn(A.sigma_d, (double)u[i])), A.dt_d);
-            x[i] = (real)__dadd_rn(__dadd_rn(xi, drift), __dmul_rn(A.sigma_d, (double)dB[i]));
-          } else {
-            const float xi = (float)x[i];
-            const float g = __fmul_rn(__fmul_rn(A.c4a_f[i], xi), __fsub_rn(__fmul_rn(xi, xi), 1.0f));
-            const float drift = __fmul_rn(__fadd_rn(-g, __fmul_rn(A.sigma_f, u[i])), A.dt_f);
-            x[i] = (real)__fadd_rn(__fadd_rn(xi, drift), __fmul_rn(A.sigma_f, dB[i]));
-          }
-        }
+        for (int i = 0; i < D; ++i) x[i] = xn[i];
         ++k;
         if (k >= lim) {
           // not detected within the pass budget: flagged, never garbage (failure row)

@@ -216,6 +216,17 @@ class DoubleWellStoppingTime1D(_DoubleWellBase):
     def get_null_action_idx(self):
         self.null_action_idx = self.get_action_idx(np.zeros((1, self.d)))
 
+    def get_hjb_solver(self, h_hjb=0.001):
+        """Reference solution on ``state_space_h`` (environments.py:392-420).  The reference loads it from the external
+        ``sde_hjb_solver`` package; here it comes from the finite-difference solve of ``hjb_1d``.  The
+        returned object has the attributes the callers read: ``u_opt`` (n_states, 1) and ``value_function``
+        (n_states,) = -log Psi, so that ``-value_function`` is the optimal value table (tabular_dp_tables.py:88)."""
+        from .hjb_1d import HJBSolution1D
+        sol = HJBSolution1D(self, h=h_hjb)
+        sol.u_opt = sol.u_opt_at(self.state_space_h).reshape(-1, 1)
+        sol.value_function = sol.value_function_at(self.state_space_h)
+        return sol
+
 
 class DoubleWellStoppingTimeND(_DoubleWellBase):
     """d-dimensional double well, target set {x_i >= 1 for all i}; d = 2 is the reference's 2-D class."""

@@ -48,15 +48,15 @@ class HJBSolution1D:
         x = np.asarray(x, dtype=np.float64)
         return np.where(x >= self.lb, 1.0, np.interp(x, self.x, self.psi))
 
-    def u_opt(self, x):
+    def u_opt_at(self, x):
         """Optimal control on arbitrary points (0 on the target set, like the reference's solution)."""
         x = np.asarray(x, dtype=np.float64)
         return np.where(x >= self.lb, 0.0, np.interp(x, self.x, self.u_opt_fine))
 
-    def value_function(self, x):
+    def value_function_at(self, x):
         x = np.asarray(x, dtype=np.float64)
         return np.where(x >= self.lb, 0.0, np.interp(x, self.x, self.value_fine))
 
     def policy_opt_table(self, env):
         """``policy_opt`` argument of test_policy_vectorized / reinforce: shape (n_states, 1) on env.state_space_h."""
-        return self.u_opt(env.state_space_h).reshape(-1, 1)
+        return self.u_opt_at(env.state_space_h).reshape(-1, 1)

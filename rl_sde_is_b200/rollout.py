@@ -167,6 +167,74 @@ def rollout_forward(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=10**6, 
     return RolloutOut(G=G, S=S, T=T, l2=l2, logw=logw, path=path, stats_dev=stats, cfg=cfg)
 
 
+@dataclass
+class Transitions:
+    """Device-resident transition stream of a rollout (float32 / bool, like the reference's ReplayBuffer arrays)."""
+    states: torch.Tensor                # [n, d]
+    actions: torch.Tensor               # [n, d]
+    rewards: torch.Tensor               # [n]
+    next_states: torch.Tensor           # [n, d]
+    done: torch.Tensor                  # [n] bool
+    counts: torch.Tensor                # [K] int64: transitions of each trajectory
+    rollout: RolloutOut = None
+
+    def __len__(self):
+        return int(self.rewards.numel())
+
+
+def rollout_transitions(env_c, mlp_c, params_host, K, *, seed=0, n_max=10**6, noise=None, traj_offset=0, K_global=None,
+                        tanh="precise", state_f64=True, order="reference", device=None):
+    """All (state, action, reward, next_state, done) tuples of K rollouts.
+
+    Two launches of K1 with the same counter-based noise: the first finds every trajectory's hit index, an exclusive
+    prefix sum of the pass counts gives each trajectory its slot range, the second streams the tuples out.
+    ``order='reference'`` returns them pass-major (all live trajectories of pass 0 in index order, then pass 1, ...), the
+    order ``sample_trajectories_buffer_vectorized`` stores them in (approximate_methods.py:513-545);
+    ``order='trajectory'`` keeps the kernel's trajectory-major layout and skips the permutation."""
+    lib = L.load()
+    if order not in ("reference", "trajectory"):
+        raise L.RlsdeError("order must be 'reference' or 'trajectory'")
+    dev = _cuda_device(device)
+    d = env_c.d
+    common = dict(seed=seed, n_steps_lim=int(n_max), noise=noise, traj_offset=traj_offset, K_global=K_global, tanh=tanh,
+                  state_f64=state_f64, want_logw=False, device=dev, kernel="thread")
+    first = rollout_forward(env_c, mlp_c, params_host, K, **common)
+    lim = int(n_max) if noise is None else min(int(n_max), int(noise.shape[0]))
+    T = first.T.to(torch.int64)
+    counts = torch.where(T >= 0, T + 1, torch.full_like(T, lim))
+    ends = torch.cumsum(counts, 0)
+    base = (ends - counts).contiguous()
+    n = int(ends[-1].item()) if K > 0 else 0
+    states = torch.empty((n, d), dtype=torch.float32, device=dev)
+    actions = torch.empty((n, d), dtype=torch.float32, device=dev)
+    next_states = torch.empty((n, d), dtype=torch.float32, device=dev)
+    rewards = torch.empty(n, dtype=torch.float32, device=dev)
+    done = torch.empty(n, dtype=torch.uint8, device=dev)
+    cfg = first.cfg
+    real = torch.float64 if state_f64 else torch.float32
+    G = torch.empty(K, dtype=real, device=dev)
+    S = torch.empty(K, dtype=real, device=dev)
+    T2 = torch.empty(K, dtype=torch.int32, device=dev)
+    stats = torch.zeros(L.RLSDE_NSTATS, dtype=torch.float64, device=dev)
+    ws = _workspace(dev)
+    if n > 0:
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = lib.rlsde_rollout_transitions(env_c, mlp_c, np.ascontiguousarray(params_host, dtype=np.float32).ctypes.data, cfg,
+                                               _ptr(noise), _ptr(base), _ptr(states), _ptr(actions), _ptr(rewards),
+                                               _ptr(next_states), _ptr(done), _ptr(G), _ptr(S), _ptr(T2), _ptr(stats),
+                                               _ptr(ws), ws.numel(), stream)
+        L.check(rc, "rlsde_rollout_transitions")
+    if order == "reference" and n > 0:
+        # pass index of every slot; a stable sort by it turns trajectory-major into the reference's pass-major order
+        k = torch.arange(n, device=dev, dtype=torch.int64) - torch.repeat_interleave(base, counts)
+        perm = torch.argsort(k, stable=True)
+        states, actions, rewards, next_states, done = (t[perm] for t in (states, actions, rewards, next_states, done))
+    out = RolloutOut(G=G, S=S, T=T2, l2=None, logw=None, path=None, stats_dev=stats, cfg=cfg)
+    return Transitions(states=states, actions=actions, rewards=rewards, next_states=next_states, done=done.bool(),
+                       counts=counts, rollout=out)
+
+
 def rollout_backward(env_c, mlp_c, params_host, fwd: RolloutOut, loss_scale, *, noise=None, device=None, balance=True):
     """K2: gradient of loss_scale * sum_k(-G_k - sg(G_k) S_k) w.r.t. the flat parameters (float32 CUDA tensor)."""
     lib = L.load()

@@ -26,6 +26,10 @@ Fixtures (all arrays little-endian, names are the keys of the .npz):
                          (reinforce_deterministic_core.py:234-243) with recorded noise.
   dp_sweeps.npz          ``q_table_update_vect`` / ``v_table_update_vect`` / ``policy_update_vect`` on the h = 0.1 tables
                          (tabular_dp_{qvalue,value,policy}_iteration.py), 3 sweeps at gamma = 1 and 0.97, and 200 sweeps.
+  replay.npz             ``sample_trajectories_buffer_vectorized`` (approximate_methods.py:513-545) into a ``ReplayBuffer``
+                         (replay_buffers.py:7-88), noise recorded from ``env.step``: 1-D (finished and n_max-capped) and 2-D.
+  formats.json           run-directory names of ``utils_path`` (:100-330) for the argument sets the tests use, and the
+                         key/dtype/shape listing of an ``agent.npz`` written by the reference's ``reinforce`` (:102-336).
   tables.npz             ``compute_r_table`` / ``compute_p_tensor_batch`` (dynamic_programming.py:3-36):
                          full tensors at h=0.1, strided sub-sample + checksums at h=0.01, and a
                          (alpha, beta) = (1, 4) case.
@@ -164,10 +168,94 @@ def dp_sweeps(env1, dp):
     print("  dp_sweeps: V(s_init) after 200 sweeps =", np.max(q[env.state_init_idx]))
 
 
+def replay_cases(env1, env2, core, am):
+    """replay.npz: buffer contents after the reference's vectorised sampler, with the increments it drew."""
+    from rl_sde_is.replay_buffers import ReplayBuffer
+    out = {}
+
+    def case(prefix, env, model, K, n_max, seed):
+        buf = ReplayBuffer(size=K * n_max, state_dim=env.d, action_dim=env.d)
+        np.random.seed(seed)
+        with NoiseRecorder(env, "step") as rec:
+            am.sample_trajectories_buffer_vectorized(env, model, buf, K, n_max)
+        n = buf.size
+        out[prefix + "noise"] = rec.stacked()
+        for name in ("states", "actions", "rewards", "next_states", "done"):
+            out[prefix + name] = getattr(buf, name)[:n].copy()
+        out[prefix + "cfg"] = np.array([K, n_max, n, buf.ptr], dtype=np.int64)
+        put_params(out, prefix, model)
+        out[prefix + "env"] = np.array([env.d, float(np.ravel(env.alpha)[0]), env.beta, env.dt], dtype=np.float64)
+        print(f"  replay {prefix}: K={K} n_max={n_max} passes={len(rec.noise)} transitions={n} done={int(buf.done[:n].sum())}")
+
+    env = env1.DoubleWellStoppingTime1D(beta=1.0, alpha=1.0, dt=0.005)
+    torch.manual_seed(3)
+    model = core.DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    model.policy[4].bias.data.fill_(1.0)
+    case("a_", env, model, 12, 5000, 41)             # every episode reaches the target set
+    torch.manual_seed(1)
+    model = core.DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    case("b_", env, model, 7, 150, 42)               # near-null policy, capped at n_max: most episodes unfinished
+    env = env2.DoubleWellStoppingTime2D(beta=1.0, alpha=1.0, dt=0.005)
+    torch.manual_seed(4)
+    model = core.DeterministicPolicy(2, 2, [32, 32], nn.Tanh())
+    model.policy[4].bias.data.fill_(1.5)
+    case("c_", env, model, 5, 5000, 43)
+    np.savez_compressed(os.path.join(OUT_DIR, "replay.npz"), **out)
+
+
+def format_cases(env1, core, dp):
+    """formats.json: directory names and the agent.npz listing produced by the reference's own I/O layer."""
+    import json
+    import rl_sde_is.utils_path as up
+    res = {"dirs": [], "agent_npz": {}}
+    env = env1.DoubleWellStoppingTime1D(beta=1.0, alpha=1.0, dt=0.005)
+    env4 = env1.DoubleWellStoppingTime1D(beta=4.0, alpha=1.0, dt=0.001)
+    for e, tag in ((env, "b1"), (env4, "b4")):
+        kw = dict(agent="reinforce-deterministic", gamma=1.0, d_hidden_layer=32, batch_size=100, lr=1e-2,
+                  n_iterations=1000, seed=1)
+        res["dirs"].append(dict(fn="get_reinforce_det_dir_path", env=tag, kwargs=kw, path=up.get_reinforce_det_dir_path(e, **kw)))
+        kw = dict(agent="reinforce-deterministic", gamma=0.99, d_hidden_layer=256, batch_size=1000, lr=1e-3,
+                  n_iterations=100, seed=None)
+        res["dirs"].append(dict(fn="get_reinforce_det_dir_path", env=tag, kwargs=kw, path=up.get_reinforce_det_dir_path(e, **kw)))
+        e.set_action_space_bounds()
+        e.discretize_state_space(0.01)
+        e.discretize_action_space(0.01)
+        res["dirs"].append(dict(fn="get_dynamic_programming_tables_dir_path", env=tag, kwargs={},
+                                path=up.get_dynamic_programming_tables_dir_path(e)))
+        kw = dict(agent="dp-q-value-iteration", n_iterations=2000)
+        res["dirs"].append(dict(fn="get_dynamic_programming_dir_path", env=tag, kwargs=kw,
+                                path=up.get_dynamic_programming_dir_path(e, **kw)))
+    data = core.reinforce(env, d_hidden_layer=32, batch_size=10, lr=1e-2, n_iterations=4, seed=1, backup_freq_iterations=2,
+                          policy_opt=np.zeros((env.n_states if hasattr(env, "n_states") else 401, 1)))
+    rel = data["rel_dir_path"]
+    root = os.path.join(up.get_data_dir(), rel)
+    res["agent_npz"]["rel_dir_path"] = rel
+    res["agent_npz"]["files"] = sorted(os.listdir(root))
+    loaded = up.load_data(rel)
+    listing = {}
+    for k, v in loaded.items():
+        if isinstance(v, np.ndarray):
+            listing[k] = ["ndarray", str(v.dtype), list(v.shape)]
+        else:
+            listing[k] = [type(v).__name__]
+    res["agent_npz"]["keys"] = listing
+    sd = torch.load(os.path.join(root, "model_n-it2"))
+    res["agent_npz"]["state_dict"] = {k: list(v.shape) for k, v in sd.items()}
+    with open(os.path.join(OUT_DIR, "formats.json"), "w") as fh:
+        json.dump(res, fh, indent=1, sort_keys=True, default=str)
+    print("  formats:", res["agent_npz"]["files"], [d["path"] for d in res["dirs"]][:3])
+
+
 def main():
     t_start = time.time()
     env1, env2, core, am, dp, tdt = import_reference()
     torch.set_num_threads(1)
+    if len(sys.argv) > 1 and sys.argv[1] == "replay":  # regenerate only the replay-buffer fixture
+        replay_cases(env1, env2, core, am)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "formats":
+        format_cases(env1, core, dp)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "dp":      # regenerate only the DP-sweep fixture
         dp_sweeps(env1, dp)
         return
@@ -320,6 +408,8 @@ def main():
     np.savez_compressed(os.path.join(OUT_DIR, "rollout_numpy_2d.npz"), **out)
 
     dp_sweeps(env1, dp)
+    replay_cases(env1, env2, core, am)
+    format_cases(env1, core, dp)
 
     for f in sorted(os.listdir(OUT_DIR)):
         if f.endswith(".npz"):

@@ -405,3 +405,75 @@ def test_qvalue_iteration_full_size_tables():
     v_init = v[env.state_init_idx[0]]
     # -log E[exp(-tau)] = 1.855 is a lower bound on the optimal expected cost (Jensen); the discretised optimum is close
     assert -2.6 < v_init < -1.7
+
+
+# ------------------------------------------------------------------------------ replay-buffer sampler
+@pytest.mark.parametrize("prefix", ["a_", "b_", "c_"])
+def test_replay_sampler_matches_reference(golden, prefix):
+    """sample_trajectories_buffer_vectorized on the recorded increments fills a ReplayBuffer like the reference does:
+    same number of tuples in the same (pass-major) order, done flags and -0.0 rewards exact, float32 values within
+    1e-5 relative (the policy is evaluated by FFMA2 dot products in another summation order than torch's)."""
+    from rl_sde_is_b200.approximate_methods import sample_trajectories_buffer_vectorized
+    from rl_sde_is_b200.replay_buffers import ReplayBuffer
+    g = golden("replay")
+    d, alpha, beta, dt = _env(g, prefix)
+    env, model = _make_env(d, alpha, beta, dt), _model_from(g, prefix, d)
+    K, n_max, n, ptr = (int(v) for v in g[prefix + "cfg"])
+    buf = ReplayBuffer(size=K * n_max, state_dim=d, action_dim=d)
+    stored = sample_trajectories_buffer_vectorized(env, model, buf, K, n_max, noise=g[prefix + "noise"])
+    assert stored == n and buf.size == n and buf.ptr == ptr
+    assert np.array_equal(buf.done[:n], g[prefix + "done"])
+    assert np.array_equal(np.signbit(buf.rewards[:n]), np.signbit(g[prefix + "rewards"]))
+    assert np.array_equal(buf.rewards[:n][g[prefix + "done"]], g[prefix + "rewards"][g[prefix + "done"]])
+    for name in ("states", "actions", "rewards", "next_states"):
+        got, want = getattr(buf, name)[:n], g[prefix + name]
+        assert got.dtype == want.dtype and got.shape == want.shape, name
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-6, err_msg=name)
+    assert abs(buf.estimate_episode_length() - g[prefix + "done"].sum() / n) < 1e-12
+    # a batch that does not fit behind the write pointer raises, as in the reference (replay_buffers.py:61-65)
+    small = ReplayBuffer(size=n - 1, state_dim=d, action_dim=d)
+    with pytest.raises(ValueError):
+        sample_trajectories_buffer_vectorized(env, model, small, K, n_max, noise=g[prefix + "noise"])
+
+
+def test_replay_sampler_rng_and_device_buffer():
+    """In-kernel RNG: the transition stream is consistent with itself (next state of pass k = state of pass k+1, one done
+    flag per finished episode, rewards = -(1 + a^2/2) dt), equals the replay of rlsde_noise_fill through the
+    injected-noise path bit for bit, and a DeviceReplayBuffer wraps around."""
+    from rl_sde_is_b200 import rollout as R
+    from rl_sde_is_b200.approximate_methods import sample_transitions, sample_trajectories_buffer_vectorized
+    from rl_sde_is_b200.replay_buffers import DeviceReplayBuffer
+    env = _make_env(1, 1.0, 1.0, 0.005)
+    torch.manual_seed(3)
+    from rl_sde_is_b200.models import DeterministicPolicy
+    model = DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    model.policy[4].bias.data.fill_(1.0)
+    K, n_max = 3000, 4000
+    tr = sample_transitions(env, model, K, n_max, seed=77, order="trajectory")
+    counts = tr.counts.cpu().numpy()
+    assert len(tr) == counts.sum() and int(tr.done.sum()) == K
+    ends = np.cumsum(counts)
+    s, a, r, ns, dn = (t.cpu().numpy() for t in (tr.states, tr.actions, tr.rewards, tr.next_states, tr.done))
+    assert dn[ends - 1].all() and dn.sum() == K                      # done exactly on the last tuple of every episode
+    inner = np.ones(len(tr), dtype=bool)
+    inner[ends - 1] = False
+    assert np.array_equal(ns[np.nonzero(inner)[0], 0], s[np.nonzero(inner)[0] + 1, 0])      # chained states
+    assert np.all(s[ends - counts, 0] == -1.0)
+    np.testing.assert_allclose(r[inner], -(1.0 + 0.5 * a[inner, 0].astype(np.float64) ** 2) * 0.005, rtol=1e-6)
+    assert np.all(r[~inner] == 0.0) and np.all(np.signbit(r[~inner]))
+    # same stream through the injected-noise path
+    noise = R.noise_fill(77, K, 1, int(counts.max()), env.dt)
+    tr2 = sample_transitions(env, model, K, n_max, noise=noise, order="trajectory")
+    for x, y in ((tr.states, tr2.states), (tr.actions, tr2.actions), (tr.rewards, tr2.rewards), (tr.next_states, tr2.next_states)):
+        assert torch.equal(x, y)
+    # pass-major order = stable sort of the trajectory-major stream by pass index
+    tr3 = sample_transitions(env, model, K, n_max, seed=77, order="reference")
+    k_idx = np.arange(len(tr)) - np.repeat(ends - counts, counts)
+    perm = np.argsort(k_idx, kind="stable")
+    assert np.array_equal(tr3.states.cpu().numpy(), s[perm]) and np.array_equal(tr3.done.cpu().numpy(), dn[perm])
+    # device-resident ring
+    ring = DeviceReplayBuffer(size=len(tr) // 2 + 5, state_dim=1, action_dim=1)
+    n_stored = sample_trajectories_buffer_vectorized(env, model, ring, K, n_max, seed=77)
+    assert n_stored == len(tr) and ring.size == ring.max_size and ring.ptr == 0
+    batch = ring.sample_batch(256)
+    assert batch["states"].is_cuda and batch["states"].shape == (256, 1) and batch["done"].dtype == torch.bool

@@ -156,3 +156,18 @@ def test_dp_sweeps_match_reference(golden):
             np.testing.assert_allclose(q, g[f"g{gi}_q{it + 1}"], rtol=0, atol=1e-13)      # BLAS vs einsum summation order
         np.testing.assert_allclose(ref.v_sweep(R, P, ts, g["v0"], gamma), g[f"g{gi}_v1"], rtol=0, atol=1e-13)
         assert np.array_equal(ref.greedy_policy_indices(R, P, ts, g["v0"], gamma, int(g["null_action_idx"][0])), g[f"g{gi}_pi1"])
+
+
+@pytest.mark.parametrize("prefix", ["a_", "b_", "c_"])
+def test_replay_transitions_match_reference(golden, prefix):
+    """oracle transitions_numpy == buffer contents written by the reference's sample_trajectories_buffer_vectorized."""
+    g = golden("replay")
+    d, alpha, beta, dt = _env(g, prefix)
+    K, n_max, n, ptr = (int(v) for v in g[prefix + "cfg"])
+    out = ref.transitions_numpy(d, alpha, beta, dt, ref.params_from_npz(g, prefix), g[prefix + "noise"], n_max)
+    assert out["rewards"].shape[0] == n == ptr
+    for name in ("states", "actions", "rewards", "next_states", "done"):
+        want = g[prefix + name]
+        assert out[name].dtype == want.dtype and out[name].shape == want.shape, name
+        assert np.array_equal(out[name], want), name
+    assert np.array_equal(np.signbit(out["rewards"]), np.signbit(g[prefix + "rewards"]))      # the -0.0 of detecting passes
