@@ -316,7 +316,7 @@ def secondary_measurements(dev):
     out = {}
     try:
         env = DoubleWellStoppingTime1D(beta=1.0, alpha=1.0, dt=0.005)
-        data = reinforce(env, d_hidden_layer=32, batch_size=100, lr=1e-2, n_iterations=30, seed=1, verbose=False, device=dev)
+        data = reinforce(env, d_hidden_layer=32, batch_size=100, lr=1e-2, n_iterations=30, seed=1, verbose=False, save=False, device=dev)
         cts = data["cts"]
         out["reinforce_config0"] = {"iter_per_s_first": 1.0 / cts[0], "iter_per_s_it10_29": float(1.0 / np.mean(cts[10:])),
                                     "mean_steps_it0": float(data["exp_time_steps"][0]),

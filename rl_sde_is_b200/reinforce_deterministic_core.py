@@ -101,17 +101,26 @@ class _LossWithAux(torch.autograd.Function):
 
 def reinforce(env, gamma=1., d_hidden_layer=256, n_layers=3, batch_size=1000, lr=1e-3, n_iterations=100, seed=None,
               test_batch_size=1000, test_freq_iterations=100, backup_freq_iterations=None, policy_opt=None,
-              load=False, test=False, live_plot=False, *, save_fn=None, verbose=True, **rollout_opts):
-    """Training loop with the reference's signature and result dictionary (:102-336).
+              load=False, test=False, live_plot=False, *, save=True, save_fn=None, verbose=True, **rollout_opts):
+    """Training loop with the reference's signature, result dictionary and on-disk layout (:102-336).
 
-    Differences that do not change results: plotting (``live_plot``) and the on-disk layout
-    (``load`` / backups through rl_sde_is.utils_path) are out of the hot path's scope; ``save_fn(data,
-    model, iteration)`` is called where the reference writes a backup.  ``gamma`` is accepted and unused,
-    as in the reference (:108-117).
+    ``agent.npz`` and the ``model_n-it{i}`` backups go to the reference's run directory (``utils_path``; pass
+    ``save=False`` to keep everything in memory); ``load=True`` returns the stored dictionary, ``load=True, test=True``
+    re-tests the stored backups like the reference.  ``save_fn(data, model, iteration)`` is an extra hook called where a
+    backup is written.  Plotting (``live_plot``) is out of the hot path's scope.  ``gamma`` is accepted and unused in
+    the loss, as in the reference (:108-117).
     """
-    if load:
-        raise NotImplementedError("loading reference run directories is outside the hot-path scope (SURVEY 8f-2)")
     from .approximate_methods import test_policy_vectorized
+    from . import utils_path as up
+
+    rel_dir_path = None
+    if save or load:
+        rel_dir_path = up.get_reinforce_det_dir_path(env, agent="reinforce-deterministic", gamma=gamma,
+                                                     d_hidden_layer=d_hidden_layer, batch_size=batch_size, lr=lr,
+                                                     n_iterations=n_iterations, seed=seed)
+    if load and not test:
+        return up.load_data(rel_dir_path)
+    stored = up.load_data(rel_dir_path) if load else None
 
     if seed is not None:
         np.random.seed(seed)
@@ -122,6 +131,11 @@ def reinforce(env, gamma=1., d_hidden_layer=256, n_layers=3, batch_size=1000, lr
     optimizer = optim.Adam(model.parameters(), lr=lr)
     data = dict(gamma=gamma, n_layers=n_layers, d_hidden_layer=d_hidden_layer, batch_size=batch_size, lr=lr,
                 n_iterations=n_iterations, seed=seed, backup_freq_iterations=backup_freq_iterations, model=model)
+    if load:
+        data = stored
+        data["model"] = model
+    if rel_dir_path is not None:
+        data["rel_dir_path"] = rel_dir_path
     returns = np.empty(0, dtype=np.float32)
     time_steps = np.empty(0, dtype=np.int32)
     losses, exp_returns, var_returns, exp_time_steps, cts = (np.full(n_iterations, np.nan) for _ in range(5))
@@ -135,35 +149,60 @@ def reinforce(env, gamma=1., d_hidden_layer=256, n_layers=3, batch_size=1000, lr
             print("it.: {:3d}, test mean return: {:2.2f}, test var return: {:.2e}, test mean time steps: {:2.2f}".format(
                 it, res[0], res[1], res[2]))
 
+    def results():
+        out = dict(returns=returns, time_steps=time_steps, losses=losses, exp_returns=exp_returns,
+                   var_returns=var_returns, exp_time_steps=exp_time_steps, cts=cts)
+        if test:
+            out.update(test_mean_returns=tests["mean_returns"], test_var_returns=tests["var_returns"],
+                       test_mean_lengths=tests["mean_lengths"], test_policy_l2_errors=tests["policy_l2_errors"])
+        return out
+
     if test:
         data.update(test_freq_iterations=test_freq_iterations, test_batch_size=test_batch_size)
+    if save:
+        up.save_data(data, rel_dir_path)
+        if not load:
+            up.save_model(model, rel_dir_path, "model_n-it{}".format(0))
+    if test:
         run_test(0)
 
     for i in range(n_iterations):
-        t0 = time.time()
-        optimizer.zero_grad()
-        eff_loss, batch_returns, batch_time_steps = sample_loss_vectorized(env, model, batch_size, **rollout_opts)
-        eff_loss.backward()
-        optimizer.step()
-        cts[i] = time.time() - t0          # wall clock of zero_grad -> loss -> backward -> step, like the reference's ct
+        if not load:
+            t0 = time.time()
+            optimizer.zero_grad()
+            eff_loss, batch_returns, batch_time_steps = sample_loss_vectorized(env, model, batch_size, **rollout_opts)
+            eff_loss.backward()
+            optimizer.step()
+            cts[i] = time.time() - t0          # wall clock of zero_grad -> loss -> backward -> step, like the reference's ct
 
-        returns = np.append(returns, batch_returns)
-        time_steps = np.append(time_steps, batch_time_steps)
-        losses[i] = float(eff_loss.detach())
-        exp_returns[i] = np.mean(batch_returns)
-        var_returns[i] = np.var(batch_returns)
-        exp_time_steps[i] = np.mean(batch_time_steps)
-        if verbose:
-            print("it.: {:2d}, loss: {:.3e}, exp return: {:.3e}, var return: {:.1e}, ct: {:.3f}".format(
-                i, losses[i], exp_returns[i], var_returns[i], cts[i]))
+            returns = np.append(returns, batch_returns)
+            time_steps = np.append(time_steps, batch_time_steps)
+            losses[i] = float(eff_loss.detach())
+            exp_returns[i] = np.mean(batch_returns)
+            var_returns[i] = np.var(batch_returns)
+            exp_time_steps[i] = np.mean(batch_time_steps)
+            if verbose:
+                print("it.: {:2d}, loss: {:.3e}, exp return: {:.3e}, var return: {:.1e}, ct: {:.3f}".format(
+                    i, losses[i], exp_returns[i], var_returns[i], cts[i]))
         if test and (i + 1) % test_freq_iterations == 0:
+            if load:
+                try:                               # re-test the stored backup of this iteration (:95-99, :267-270)
+                    up.load_model(model, rel_dir_path, "model_n-it{}".format(i + 1))
+                except FileNotFoundError:
+                    print("there is no backup for iteration {:d}".format(i + 1))
             run_test(i + 1)
-        if backup_freq_iterations is not None and (i + 1) % backup_freq_iterations == 0 and save_fn is not None:
-            save_fn(data, model, i + 1)
+        if not load and backup_freq_iterations is not None and (i + 1) % backup_freq_iterations == 0:
+            if save:
+                up.save_model(model, rel_dir_path, "model_n-it{}".format(i + 1))
+                data.update(results())
+                up.save_data(data, rel_dir_path)
+            if save_fn is not None:
+                save_fn(data, model, i + 1)
 
-    data.update(returns=returns, time_steps=time_steps, losses=losses, exp_returns=exp_returns,
-                var_returns=var_returns, exp_time_steps=exp_time_steps, cts=cts)
-    if test:
-        data.update(test_mean_returns=tests["mean_returns"], test_var_returns=tests["var_returns"],
-                    test_mean_lengths=tests["mean_lengths"], test_policy_l2_errors=tests["policy_l2_errors"])
+    if not load:
+        data.update(results())
+    elif test:
+        data.update({k: v for k, v in results().items() if k.startswith("test_")})
+    if save:
+        up.save_data(data, rel_dir_path)
     return data

@@ -94,7 +94,8 @@ def get_iter_str(**kwargs):
 
 
 def get_seed_str(**kwargs):
-    return "seed{}".format(kwargs["seed"]) if "seed" in kwargs else ""
+    seed = kwargs.get("seed")
+    return "seed{:1d}".format(seed) if seed else "seedNone"       # seed 0 also prints as None, like the reference (:135-140)
 
 
 def get_dynamic_programming_tables_dir_path(env):
@@ -103,7 +104,7 @@ def get_dynamic_programming_tables_dir_path(env):
 
 
 def get_dynamic_programming_dir_path(env, **kwargs):
-    param_str = "h-state{:.0e}_h-action{:.0e}_dt{:.0e}_".format(env.h_state, env.h_action, env.dt) + get_iter_str(**kwargs)
+    param_str = "h-state{:.0e}_h-action{:.0e}_dt{:.0e}_n-it{:.0e}".format(env.h_state, env.h_action, env.dt, kwargs["n_iterations"])
     return get_rel_dir_path(env, kwargs["agent"], param_str)
 
 

@@ -1,0 +1,95 @@
+"""Host-side rows of SURVEY 8f: on-disk formats (8f-2) and the 1-D HJB reference solution (8f-3).  CPU only."""
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _env_like(tag):
+    """Attribute bag with what utils_path / hjb_1d read from an env (no CUDA needed)."""
+    beta, dt = (1.0, 0.005) if tag == "b1" else (4.0, 0.001)
+    return SimpleNamespace(name="doublewell-1d-st__beta{:.1f}_alpha{:.1f}".format(beta, 1.0), beta=beta, alpha=1.0, dt=dt,
+                           sigma=np.sqrt(2.0 / beta), lb=1.0, rb=2.0, h_state=0.01, h_action=0.01, is_state_init_sampled=False,
+                           state_init=-np.ones((1, 1), dtype=np.float32))
+
+
+def test_run_directory_names_match_reference(tmp_path):
+    """Directory strings recorded from the reference's utils_path (tests/golden/formats.json)."""
+    from rl_sde_is_b200 import utils_path as up
+    up.set_data_dir(tmp_path)
+    with open(os.path.join(GOLDEN, "formats.json")) as fh:
+        fx = json.load(fh)
+    assert len(fx["dirs"]) >= 8
+    for case in fx["dirs"]:
+        env = _env_like(case["env"])
+        fn = getattr(up, case["fn"])
+        got = fn(env, **case["kwargs"]) if case["kwargs"] else fn(env)
+        assert got == case["path"], case
+        assert os.path.isdir(os.path.join(tmp_path, got))        # created, like the reference's get_rel_dir_path
+
+
+def test_agent_npz_and_model_round_trip(tmp_path):
+    """save_data / load_data / save_model / load_model: same file names, key set and unwrapping as the reference's."""
+    from rl_sde_is_b200 import utils_path as up
+    from rl_sde_is_b200.models import DeterministicPolicy
+    up.set_data_dir(tmp_path)
+    with open(os.path.join(GOLDEN, "formats.json")) as fh:
+        fx = json.load(fh)["agent_npz"]
+    env = _env_like("b1")
+    rel = up.get_reinforce_det_dir_path(env, agent="reinforce-deterministic", gamma=1.0, d_hidden_layer=32, batch_size=10,
+                                        lr=1e-2, n_iterations=4, seed=1)
+    assert rel == fx["rel_dir_path"]
+    torch.manual_seed(1)
+    model = DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    data = dict(gamma=1.0, n_layers=3, d_hidden_layer=32, batch_size=10, lr=1e-2, n_iterations=4, seed=1,
+                backup_freq_iterations=2, model=model, rel_dir_path=rel,
+                returns=np.zeros(40, np.float32), time_steps=np.zeros(40), losses=np.zeros(4), exp_returns=np.zeros(4),
+                var_returns=np.zeros(4), exp_time_steps=np.zeros(4), cts=np.zeros(4))
+    up.save_data(data, rel)
+    for it in (0, 2, 4):
+        up.save_model(model, rel, "model_n-it{}".format(it))
+    assert sorted(os.listdir(os.path.join(tmp_path, rel))) == fx["files"]
+    back = up.load_data(rel)
+    assert set(back) == set(fx["keys"])
+    for key, spec in fx["keys"].items():
+        if spec[0] == "ndarray":
+            assert isinstance(back[key], np.ndarray) and str(back[key].dtype) == spec[1] and list(back[key].shape) == spec[2], key
+        else:
+            assert type(back[key]).__name__ == spec[0], key
+    sd = torch.load(os.path.join(tmp_path, rel, "model_n-it2"))
+    assert {k: list(v.shape) for k, v in sd.items()} == fx["state_dict"]
+    other = DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    up.load_model(other, rel, "model_n-it2")
+    assert all(torch.equal(a, b) for a, b in zip(other.state_dict().values(), model.state_dict().values()))
+    with pytest.raises(FileNotFoundError):
+        up.load_data("no/such/run")
+
+
+@pytest.mark.parametrize("beta", [1.0, 4.0])
+def test_hjb_solution_properties(beta):
+    """Psi solves (1/beta) Psi'' - V' Psi' - Psi = 0 with Psi = 1 on the target set; u* = sigma Psi'/Psi; V* = -log Psi."""
+    from rl_sde_is_b200.hjb_1d import HJBSolution1D
+    env = SimpleNamespace(beta=beta, alpha=1.0, lb=1.0, sigma=np.sqrt(2.0 / beta))
+    fine, coarse = HJBSolution1D(env, h=5e-4), HJBSolution1D(env, h=1e-3)
+    x, psi, h = fine.x, fine.psi, 5e-4
+    res = (1 / beta) * (psi[2:] - 2 * psi[1:-1] + psi[:-2]) / h ** 2 \
+        - 4 * x[1:-1] * (x[1:-1] ** 2 - 1) * (psi[2:] - psi[:-2]) / (2 * h) - psi[1:-1]
+    assert np.abs(res).max() < 1e-6
+    assert psi[-1] == 1.0 and np.all(np.diff(psi[x > -1.5]) > 0) and np.all((psi > 0) & (psi <= 1))
+    pts = np.array([-1.5, -1.0, -0.5, 0.0, 0.5, 0.9])
+    np.testing.assert_allclose(coarse.psi_at(pts), fine.psi_at(pts), rtol=2e-5)           # second-order convergence
+    np.testing.assert_allclose(coarse.u_opt_at(pts), fine.u_opt_at(pts), rtol=1e-4)
+    np.testing.assert_allclose(fine.value_function_at(pts), -np.log(fine.psi_at(pts)), rtol=1e-12)
+    far = HJBSolution1D(env, h=1e-3, x_min=-4.0)                                          # left boundary placement is immaterial
+    np.testing.assert_allclose(far.psi_at(pts), coarse.psi_at(pts), rtol=1e-8)
+    assert np.all(fine.u_opt_at(np.array([1.0, 1.5, 2.0])) == 0.0) and np.all(fine.psi_at(np.array([1.0, 2.0])) == 1.0)
+    # known values: continuous-time Psi(-1); the time-discretised Monte-Carlo estimates (0.1565 at dt = 0.005;
+    # 0.00543 at beta = 4, dt = 0.001, profiles/r01) sit a few per cent below because discrete monitoring misses crossings
+    expect = {1.0: 0.164016, 4.0: 0.005496}[beta]
+    assert abs(fine.psi_at(-1.0) - expect) / expect < 1e-4

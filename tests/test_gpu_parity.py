@@ -4,6 +4,8 @@ Tolerances (BASELINE.json north_star): injected-noise trajectories within 1e-5 r
 functionals, hit indices exact; tables within 1e-6 (we hold 1e-13); in-kernel RNG statistically
 indistinguishable (and, against the C restatement of the same Philox stream, per-trajectory close).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -477,3 +479,62 @@ def test_replay_sampler_rng_and_device_buffer():
     assert n_stored == len(tr) and ring.size == ring.max_size and ring.ptr == 0
     batch = ring.sample_batch(256)
     assert batch["states"].is_cuda and batch["states"].shape == (256, 1) and batch["done"].dtype == torch.bool
+
+
+# ------------------------------------------------------------------------------ SURVEY 8f-2 / 8f-3 on the device path
+def test_optimal_tables_from_hjb_solution(golden):
+    """compute_optimal_{q,v}_table (tabular_dp_tables.py:19-42) with the HJB value function: equal to the reference's NumPy
+    expression on the reference's own h = 0.1 tables; and the discrete chain agrees with the continuous solution."""
+    from rl_sde_is_b200.environments import DoubleWellStoppingTime1D
+    from rl_sde_is_b200.tabular_dp_tables import compute_optimal_q_table, compute_optimal_v_table
+    from rl_sde_is_b200.tabular_dp_sweeps import qvalue_iteration
+    g = golden("tables")
+    env = DoubleWellStoppingTime1D(beta=1.0, alpha=1.0, dt=0.005)
+    env.set_action_space_bounds()
+    env.discretize_state_space(0.1)
+    env.discretize_action_space(0.1)
+    sol = env.get_hjb_solver()
+    assert sol.u_opt.shape == (env.n_states, 1) and sol.value_function.shape == (env.n_states,)
+    v_opt, P, R = -sol.value_function, g["h01_P"], g["h01_R"]
+    d = np.where(env.is_in_ts, 1, 0)[:, None]
+    q_ref = (1 - d) * np.dot(np.moveaxis(P, 0, -1), v_opt) + R                            # tabular_dp_tables.py:35-41
+    q = compute_optimal_q_table(env, R, P, v_opt, sol.u_opt)
+    np.testing.assert_allclose(q, q_ref, rtol=1e-12, atol=1e-13)
+    a_idx = env.get_action_idx(sol.u_opt)
+    v = compute_optimal_v_table(env, R, P, v_opt, sol.u_opt)
+    np.testing.assert_allclose(v, q_ref[np.arange(env.n_states), a_idx], rtol=1e-12, atol=1e-13)
+    # value iteration on the fine tables converges to the time-discretised value: within 5 % of -(-log Psi) at x0 = -1
+    env.discretize_state_space(0.01)
+    env.discretize_action_space(0.01)
+    sol = env.get_hjb_solver()
+    out = qvalue_iteration(env, gamma=1.0, n_iterations=1500)
+    i0 = int(env.get_state_idx(env.state_init)[0])
+    assert abs(out["v_table"][i0] - (-sol.value_function[i0])) < 0.05 * abs(sol.value_function[i0])
+    greedy = env.action_space_h[out["greedy_action_idx"]]
+    inner = (env.state_space_h > -1.5) & (env.state_space_h < 0.8)
+    assert np.abs(greedy[inner] - sol.u_opt[inner, 0]).max() < 0.15                       # greedy action ~ HJB control
+
+
+def test_reinforce_writes_and_loads_reference_layout(tmp_path):
+    """reinforce() leaves agent.npz + model_n-it{i} in the reference's run directory; load=True reads them back;
+    load=True, test=True re-tests the stored backups; test_policy_vectorized takes the HJB policy table."""
+    from rl_sde_is_b200 import utils_path as up
+    from rl_sde_is_b200.environments import DoubleWellStoppingTime1D
+    from rl_sde_is_b200.reinforce_deterministic_core import reinforce
+    up.set_data_dir(tmp_path)
+    env = DoubleWellStoppingTime1D(beta=1.0, alpha=1.0, dt=0.005)
+    env.discretize_state_space(0.05)
+    policy_opt = env.get_hjb_solver().u_opt
+    kw = dict(d_hidden_layer=32, batch_size=16, lr=1e-2, n_iterations=4, seed=1, backup_freq_iterations=2, verbose=False)
+    data = reinforce(env, test=True, test_batch_size=64, test_freq_iterations=2, policy_opt=policy_opt, **kw)
+    rel = data["rel_dir_path"]
+    assert rel == "doublewell-1d-st__beta1.0_alpha1.0/reinforce-deterministic/init-state-1.0_gamma1.000_hidden-size32_K2e+01_lr1.0e-02_n-iter4e+00_seed1"
+    assert sorted(os.listdir(os.path.join(tmp_path, rel))) == ["agent.npz", "model_n-it0", "model_n-it2", "model_n-it4"]
+    assert data["test_policy_l2_errors"].shape == (3,) and np.all(np.isfinite(data["test_policy_l2_errors"]))
+    back = reinforce(env, load=True, **kw)
+    for key in ("returns", "time_steps", "losses", "exp_returns", "var_returns", "exp_time_steps", "cts", "test_mean_returns"):
+        assert np.array_equal(back[key], data[key]), key
+    assert back["returns"].dtype == np.float32 and back["time_steps"].dtype == np.float64 and back["seed"] == 1
+    assert type(back["model"]).__name__ == "DeterministicPolicy"
+    again = reinforce(env, load=True, test=True, test_batch_size=64, test_freq_iterations=2, policy_opt=policy_opt, **kw)
+    assert again["test_mean_returns"].shape == (3,) and np.array_equal(again["losses"], data["losses"])

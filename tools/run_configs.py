@@ -54,7 +54,7 @@ def main():
     # ---------------------------------------------------------------- config 0
     if "0" not in skip and rank == 0:
         env = DoubleWellStoppingTime1D(beta=1.0, alpha=1.0, dt=0.005)
-        data = reinforce(env, d_hidden_layer=32, batch_size=100, lr=1e-2, n_iterations=a.iters0, seed=1, verbose=False, device=dev)
+        data = reinforce(env, d_hidden_layer=32, batch_size=100, lr=1e-2, n_iterations=a.iters0, seed=1, verbose=False, save=False, device=dev)
         cts = data["cts"]
         emit({"config": 0, "what": "REINFORCE K=100 lr=1e-2 seed=1", "iterations": a.iters0,
               "iter_per_s_it0": 1 / cts[0], "iter_per_s_it10_29": 1 / np.mean(cts[10:30]), "iter_per_s_last20": 1 / np.mean(cts[-20:]),
