@@ -71,31 +71,67 @@ __global__ void __launch_bounds__(128) tables_kernel(const double* __restrict__ 
 }
 
 // ---- fast path: uniform state grid with fine cells (cell width <= 0.25 sd) -------------------------------
-// P_cell = integral of the N(0,1) density over [t, t + dcell]: 4-point Gauss-Legendre (error < 1e-13 at
-// dcell = 0.25) with the density at the nodes advanced from cell to cell by the multiplicative recurrence
-//     phi(t + ds) = phi(t) * r,   r(t) = exp(-t ds - ds^2 / 2),   r(t + ds) = r(t) * exp(-ds^2)
-// and re-anchored with exact exp() every GL_ANCHOR cells (measured |P - reference formula| <= 5e-15 at config 3,
-// tests/test_gpu_parity.py holds 1e-13).  ~14 FP64 operations per entry instead of ~100 for erf/erfc, which moves
-// the kernel from the FP64 pipe towards the HBM write roofline.  One thread owns one (s, a) column and walks s'.
+// P_cell = integral of the N(0,1) density over the cell [m - D/2, m + D/2] by 4-point Gauss-Legendre (error < 1e-13 at
+// D = 0.25).  The nodes sit symmetrically at m +- a, m +- b, and phi(m +- o) = phi(m) exp(-o^2/2) exp(-+ m o), so
+//     P = phi(m) * (Ya + Yb),   Ya = 2 D w_a exp(-a^2/2) cosh(m a),   Yb likewise with (w_b, b).
+// Walking s' moves m by the constant step ds, and all three factors follow cheap recurrences:
+//     phi(m + ds) = phi(m) r,   r <- r exp(-ds^2)                                (2 DMUL)
+//     Y(m + ds)   = Y + dY,     dY <- dY + 4 sinh^2(o ds / 2) Y(m + ds)          (DADD + DFMA each; the second-difference
+//                                                                                 form of cosh's three-term recurrence,
+//                                                                                 stable because the small quantity is kept)
+// 8 FP64 operations and one 8-byte store per entry, re-anchored with exact exp() every GL_ANCHOR cells (measured
+// |P - reference formula| <= 5e-15 at config 3; tests hold 1e-13).  One thread owns one (s, a) column of one
+// GL_ANCHOR-row chunk; columns are the flat index s * Na + a, so every lane of every warp is busy and a block stores
+// 1 KB of contiguous bytes per row.
 constexpr int GL_ANCHOR = 64;
+
+struct GlConst {
+  double inv_sd, dcell, dstep, rho;        // 1/sd, D, ds, exp(-ds^2)
+  double off_a, off_b;                     // node offsets a, b
+  double coef_a, coef_b;                   // 2 D w exp(-o^2/2)
+  double mu_a, mu_b;                       // 4 sinh^2(o ds / 2)
+  double sh_a, sh_b;                       // sinh(o ds / 2)
+  double eh_a, eh_b;                       // exp(o ds / 2)
+  double half_ds2;                         // ds^2 / 2
+};
 
 __global__ void __launch_bounds__(128) tables_gl_kernel(const double* __restrict__ sgrid, long long Ns,
                                                         const double* __restrict__ agrid, long long Na,
                                                         const unsigned char* __restrict__ in_ts, double inv_nts,
                                                         double alpha, double sigma, double dt, double h,
                                                         long long sp_begin, long long sp_end, double* __restrict__ P) {
-  const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long s = blockIdx.y;
-  if (a >= Na) return;
-  // blockIdx.z picks one anchor-aligned chunk of GL_ANCHOR next-states: many equal work items instead of one
-  // long column per thread, so the grid spreads evenly over the SMs (2005 long blocks ran as 1.4 waves)
-  const long long chunk_lo = (sp_begin / GL_ANCHOR + blockIdx.z) * GL_ANCHOR;
+  // constants of the recurrences: the same for every column, computed once per block from the grid end points
+  __shared__ GlConst C;
+  if (threadIdx.x == 0) {
+    C.inv_sd = 1.0 / (sigma * sqrt(dt));
+    C.dcell = 2.0 * h * C.inv_sd;
+    C.dstep = (sgrid[Ns - 1] - sgrid[0]) / (double)(Ns - 1) * C.inv_sd;
+    C.rho = exp(-C.dstep * C.dstep);
+    C.half_ds2 = 0.5 * C.dstep * C.dstep;
+    C.off_a = 0.4305681557970263 * C.dcell;
+    C.off_b = 0.1699905217924281 * C.dcell;
+    C.coef_a = 2.0 * C.dcell * 0.1739274225687269 * exp(-0.5 * C.off_a * C.off_a);
+    C.coef_b = 2.0 * C.dcell * 0.3260725774312731 * exp(-0.5 * C.off_b * C.off_b);
+    C.sh_a = sinh(0.5 * C.off_a * C.dstep);
+    C.sh_b = sinh(0.5 * C.off_b * C.dstep);
+    C.mu_a = 4.0 * C.sh_a * C.sh_a;
+    C.mu_b = 4.0 * C.sh_b * C.sh_b;
+    C.eh_a = exp(0.5 * C.off_a * C.dstep);
+    C.eh_b = exp(0.5 * C.off_b * C.dstep);
+  }
+  __syncthreads();
+  const long long stride = Ns * Na;
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= stride) return;
+  const long long s = c / Na, a = c - s * Na;
+  // blockIdx.y picks one anchor-aligned chunk of GL_ANCHOR next-states: many equal work items instead of one
+  // long column per thread, so the grid spreads evenly over the SMs
+  const long long chunk_lo = (sp_begin / GL_ANCHOR + blockIdx.y) * GL_ANCHOR;
   const long long slab_begin = sp_begin;
   sp_begin = chunk_lo > sp_begin ? chunk_lo : sp_begin;
   sp_end = chunk_lo + GL_ANCHOR < sp_end ? chunk_lo + GL_ANCHOR : sp_end;
   if (sp_begin >= sp_end) return;
-  const long long stride = Ns * Na;
-  double* out = P + (sp_begin - slab_begin) * stride + s * Na + a;     // P points at row slab_begin
+  double* out = P + (sp_begin - slab_begin) * stride + c;              // P points at row slab_begin
   if (in_ts[s]) {
     for (long long sp = sp_begin; sp < sp_end; ++sp, out += stride) *out = in_ts[sp] ? inv_nts : 0.0;
     return;
@@ -104,38 +140,35 @@ __global__ void __launch_bounds__(128) tables_gl_kernel(const double* __restrict
   const double act = agrid[a];
   const double grad = __dmul_rn(__dmul_rn(__dmul_rn(4.0, alpha), xs), __dsub_rn(__dmul_rn(xs, xs), 1.0));
   const double mu = __dadd_rn(xs, __dmul_rn(__dadd_rn(-grad, __dmul_rn(sigma, act)), dt));
-  const double sd = __dmul_rn(sigma, sqrt(dt));
-  const double inv_sd = 1.0 / sd;
   // anchors sit at absolute multiples of GL_ANCHOR, so a slab holds exactly the entries of the full tensor
-  const long long sp_first = (sp_begin / GL_ANCHOR) * GL_ANCHOR;
-  const double dcell = 2.0 * h * inv_sd;                                   // integration width of a cell
-  const double dstep = (sgrid[Ns - 1] - sgrid[0]) / (double)(Ns - 1) * inv_sd;   // advance between cells
-  const double rho = exp(-dstep * dstep);
-  const double c0 = 0.5 - 0.4305681557970263, c1 = 0.5 - 0.1699905217924281;
-  const double c2 = 0.5 + 0.1699905217924281, c3 = 0.5 + 0.4305681557970263;
-  const double w0 = 0.1739274225687269 * dcell, w1 = 0.3260725774312731 * dcell;
-  const double kInvSqrt2Pi = 0.3989422804014327;
-  double p0 = 0, p1 = 0, p2 = 0, p3 = 0, r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-  for (long long sp = sp_first; sp < sp_end; ++sp) {
-    if ((sp % GL_ANCHOR) == 0) {
-      const double tl = (sgrid[sp] - h - mu) * inv_sd;
-      const double t0 = fma(c0, dcell, tl), t1 = fma(c1, dcell, tl), t2 = fma(c2, dcell, tl), t3 = fma(c3, dcell, tl);
-      const double hs = -0.5 * dstep * dstep;
-      p0 = kInvSqrt2Pi * exp(-0.5 * t0 * t0); r0 = exp(fma(-t0, dstep, hs));
-      p1 = kInvSqrt2Pi * exp(-0.5 * t1 * t1); r1 = exp(fma(-t1, dstep, hs));
-      p2 = kInvSqrt2Pi * exp(-0.5 * t2 * t2); r2 = exp(fma(-t2, dstep, hs));
-      p3 = kInvSqrt2Pi * exp(-0.5 * t3 * t3); r3 = exp(fma(-t3, dstep, hs));
-    }
-    if (sp >= sp_begin) {
-      double p = fma(w0, p0 + p3, w1 * (p1 + p2));
-      if (sp == 0) p += ndtr((sgrid[0] - h - mu) * inv_sd);                   // left tail folded into the first row
-      if (sp == Ns - 1) p += 1.0 - ndtr((sgrid[Ns - 1] + h - mu) * inv_sd);   // right tail folded into the last row
-      *out = p;
-      out += stride;
-    }
-    p0 *= r0; p1 *= r1; p2 *= r2; p3 *= r3;
-    r0 *= rho; r1 *= rho; r2 *= rho; r3 *= rho;
+  const double m = fma(sgrid[chunk_lo] - h - mu, C.inv_sd, 0.5 * C.dcell);       // midpoint of cell chunk_lo
+  double phi = 0.3989422804014327 * exp(-0.5 * m * m);
+  double r = exp(-fma(m, C.dstep, C.half_ds2));
+  const double ea = exp(m * C.off_a), eb = exp(m * C.off_b);
+  const double ia = 1.0 / ea, ib = 1.0 / eb;
+  double ya = C.coef_a * (0.5 * (ea + ia)), yb = C.coef_b * (0.5 * (eb + ib));
+  // first difference: cosh((m + ds) o) - cosh(m o) = 2 sinh((m + ds/2) o) sinh(ds o / 2)
+  double da = C.coef_a * ((ea * C.eh_a - ia / C.eh_a) * C.sh_a);
+  double db = C.coef_b * ((eb * C.eh_b - ib / C.eh_b) * C.sh_b);
+  const double rho = C.rho, mua = C.mu_a, mub = C.mu_b;
+  for (long long sp = chunk_lo; sp < sp_begin; ++sp) {      // a slab that starts inside a chunk: advance without storing
+    phi *= r; r *= rho;
+    ya += da; da = fma(mua, ya, da);
+    yb += db; db = fma(mub, yb, db);
   }
+  double* const first = out;
+  const int n = (int)(sp_end - sp_begin);
+#pragma unroll 8
+  for (int j = 0; j < n; ++j) {
+    *out = phi * (ya + yb);
+    out += stride;
+    phi *= r; r *= rho;
+    ya += da; da = fma(mua, ya, da);
+    yb += db; db = fma(mub, yb, db);
+  }
+  // tails folded into the first and the last row of the grid (environments.py:97-101)
+  if (sp_begin == 0) *first += ndtr((sgrid[0] - h - mu) * C.inv_sd);
+  if (sp_end == Ns) *(out - stride) += 1.0 - ndtr((sgrid[Ns - 1] + h - mu) * C.inv_sd);
 }
 
 __global__ void rtable_kernel(long long Ns, const double* __restrict__ agrid, long long Na,
@@ -156,10 +189,10 @@ int launch_tables(const double* state_grid, long long Ns, const double* action_g
   const double dcell = 2.0 * h_half / (sigma * sqrt(dt));
   if (P && sprime_end > sprime_begin && uniform_grid && Ns >= 2 && dcell <= 0.25) {
     const long long n_chunks = (sprime_end - 1) / GL_ANCHOR - sprime_begin / GL_ANCHOR + 1;
-    dim3 grid((unsigned)((Na + 127) / 128), (unsigned)Ns, (unsigned)n_chunks);
+    const long long cols = Ns * Na;
+    dim3 grid((unsigned)((cols + 127) / 128), (unsigned)n_chunks);
     tables_gl_kernel<<<grid, 128, 0, stream>>>(state_grid, Ns, action_grid, Na, in_ts, n_ts > 0 ? 1.0 / (double)n_ts : 0.0,
-                                               alpha, sigma, dt, h_half, sprime_begin, sprime_end,
-                                               P);
+                                               alpha, sigma, dt, h_half, sprime_begin, sprime_end, P);
   } else if (P && sprime_end > sprime_begin) {
     const long long nsp = sprime_end - sprime_begin;
     dim3 grid((unsigned)((Na + 127) / 128), (unsigned)Ns, (unsigned)((nsp + TABLE_TILE - 1) / TABLE_TILE));

@@ -17,13 +17,24 @@ from .rollout import _cuda_device, _ptr
 
 
 def _device_grids(env, dev):
-    sg = torch.as_tensor(np.ascontiguousarray(env.state_space_h, dtype=np.float64), device=dev)
-    ag = torch.as_tensor(np.ascontiguousarray(env.action_space_h, dtype=np.float64), device=dev)
-    ts = torch.as_tensor(np.ascontiguousarray(env.is_in_ts, dtype=np.uint8), device=dev)
-    return sg, ag, ts
+    """The env's grids on the device, uploaded once per (env, grids) and kept on the env object: three small pageable
+    host-to-device copies per call would otherwise serialise the host with the stream."""
+    sg_h = np.ascontiguousarray(env.state_space_h, dtype=np.float64)
+    ag_h = np.ascontiguousarray(env.action_space_h, dtype=np.float64)
+    ts_h = np.ascontiguousarray(env.is_in_ts, dtype=np.uint8)
+    key = (str(dev), sg_h.tobytes(), ag_h.tobytes(), ts_h.tobytes())
+    cached = getattr(env, "_rlsde_device_grids", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    grids = tuple(torch.as_tensor(a, device=dev) for a in (sg_h, ag_h, ts_h))
+    try:
+        env._rlsde_device_grids = (key, grids)
+    except AttributeError:
+        pass
+    return grids
 
 
-def _tables(env, want_p, want_r, device, sprime_range=None, exact_cdf=False):
+def _tables(env, want_p, want_r, device, sprime_range=None, exact_cdf=False, out=None):
     if env.d != 1:
         raise L.RlsdeError("the tabular builder covers the 1-D environment (as the reference's does)")
     lib = L.load()
@@ -33,7 +44,11 @@ def _tables(env, want_p, want_r, device, sprime_range=None, exact_cdf=False):
     lo, hi = (0, Ns) if sprime_range is None else (int(sprime_range[0]), int(sprime_range[1]))
     grid = np.asarray(env.state_space_h, dtype=np.float64)
     uniform = int(Ns >= 2 and np.abs(grid - (grid[0] + np.arange(Ns) * (grid[-1] - grid[0]) / (Ns - 1))).max() <= 1e-14 and not exact_cdf)
-    P = torch.empty((hi - lo, Ns, Na), dtype=torch.float64, device=dev) if want_p else None
+    P = None
+    if want_p:
+        P = out if out is not None else torch.empty((hi - lo, Ns, Na), dtype=torch.float64, device=dev)
+        if tuple(P.shape) != (hi - lo, Ns, Na) or P.dtype != torch.float64 or P.device != dev or not P.is_contiguous():
+            raise L.RlsdeError(f"out must be a contiguous float64 tensor of shape {(hi - lo, Ns, Na)} on {dev}")
     Rt = torch.empty((Ns, Na), dtype=torch.float64, device=dev) if want_r else None
     with torch.cuda.device(dev):
         rc = lib.rlsde_tables(_ptr(sg), Ns, _ptr(ag), Na, _ptr(ts), int(env.is_in_ts.sum()), float(env.alpha),
@@ -49,14 +64,15 @@ def compute_r_table(env, *, device=None, device_out=False):
     return Rt if device_out else Rt.cpu().numpy()
 
 
-def compute_p_tensor_batch(env, *, device=None, device_out=False, sprime_range=None, exact_cdf=False):
+def compute_p_tensor_batch(env, *, device=None, device_out=False, sprime_range=None, exact_cdf=False, out=None):
     """P[s', s, a] (float64, shape (n_states, n_states, n_actions), action innermost).
 
     ``sprime_range=(begin, end)`` builds only that slab of next-states (multi-GPU sharding).
     ``exact_cdf=True`` forces two erf/erfc evaluations per cell edge (the reference's formula literally) instead of
-    the quadrature fast path used on fine uniform grids; both agree with the reference to < 1e-13."""
-    P, _ = _tables(env, True, False, device, sprime_range, exact_cdf)
-    return P if device_out else P.cpu().numpy()
+    the quadrature fast path used on fine uniform grids; both agree with the reference to < 1e-13.
+    ``out``: preallocated CUDA tensor to build into (implies ``device_out``)."""
+    P, _ = _tables(env, True, False, device, sprime_range, exact_cdf, out)
+    return P if (device_out or out is not None) else P.cpu().numpy()
 
 
 def p_tensor_column_sums(P_dev):
