@@ -81,9 +81,9 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     import torch
-    K = 4000
+    K = 50000                      # ~3 s of host work per step: larger batches vectorise better, to the reference's advantage
     for _ in range(args.warmup):
-        cpu_port_python(500)
+        cpu_port_python(2000)
     vals, useful_tot, wall_tot, threads = [], 0, 0.0, 1
     for s in range(args.steps):
         v, useful, wall, threads = cpu_port_python(K, seed=s)
@@ -210,6 +210,7 @@ def run_gpu_arm(args):
 
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     stats_steps = []
+    launches0 = L.load().rlsde_launch_count()
     with ClockSampler(local_rank) as clk:
         wall0 = time.perf_counter()
         for s in range(args.steps):
@@ -219,6 +220,7 @@ def run_gpu_arm(args):
             ev[s][1].record()
         torch.cuda.synchronize()
         wall1 = time.perf_counter()
+    gpu_launches = int(L.load().rlsde_launch_count() - launches0)    # this library's kernels inside the timed region
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -265,7 +267,7 @@ def run_gpu_arm(args):
     per_gpu_steps = useful / n_gpus / (dev_ms * 1e-3)
     achieved = per_gpu_steps * FLOP_PER_STEP / 1e12
     roofline = {"bound": "fp32_cuda_core", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                "frac": achieved / peak_tflops, "traffic": None,
+                "frac": achieved / peak_tflops, "traffic": 1.61e6, "traffic_unit": "bytes per launch (dram read + write, ncu --set full, profiles/r01)",
                 "note": f"peak = {sm} SMs x 128 FMA lanes x 2 x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json; FFMA "
                         f"microbenchmark in profiles/ confirms 128 lanes/clk/SM); algorithmic work {FLOP_PER_STEP} FLOP per useful "
                         "trajectory-step (SURVEY 8d), timed per launch with CUDA events incl. the statistics reduction; the "
@@ -276,9 +278,11 @@ def run_gpu_arm(args):
              "wall_ms_per_step_incl_flush": 1e3 * (wall1 - wall0) / args.steps, "tanh": args.tanh}
     cpu_baseline = None
     if n_gpus == 1 and not args.no_cpu_baseline:
-        v, u, w, thr = cpu_port_python(4000)
+        cpu_port_python(2000)                             # warm-up (thread pools, allocator)
+        ck = 100000
+        v, u, w, thr = cpu_port_python(ck)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": thr, "kind": "port", "host_cores": os.cpu_count(),
-                        "sample": f"4000 trajectories x n_steps_lim {lim} ({u} useful steps, {w:.1f} s): the reference's per-pass "
+                        "sample": f"{ck} trajectories x n_steps_lim {lim} ({u} useful steps, {w:.1f} s): the reference's per-pass "
                                   "torch forward + NumPy step loop (oracle/reference_semantics.py)"}
         try:
             vc, uc, wc, thc = cpu_port_c(200000)
@@ -298,7 +302,7 @@ def run_gpu_arm(args):
                 "d2h_bytes_per_step": int(L.RLSDE_NSTATS * 8),
                 "note": "is_estimate(env, model, K): host policy parameters travel as kernel arguments, the 16-double statistics "
                         "record comes back; wall clock around the call"},
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": gpu_launches,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "extra": extra,
     }
     print(json.dumps(line), flush=True)

@@ -135,6 +135,8 @@ int rlsde_version(void);
 const char* rlsde_strerror(int status);
 /* text of the last CUDA error seen by this thread's calls ("" if none) */
 const char* rlsde_last_cuda_error(void);
+/* kernels this library has launched in this process so far (diagnostics: bench.py's gpu_launches) */
+long long rlsde_launch_count(void);
 /* SM count and compute capability of the current device */
 int rlsde_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 /* 1 if a fused kernel is compiled for this policy shape */

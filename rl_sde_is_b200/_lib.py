@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = [
     "rlsde_version", "rlsde_strerror", "rlsde_last_cuda_error", "rlsde_device_info", "rlsde_supported",
     "rlsde_param_count", "rlsde_workspace_bytes", "rlsde_rollout_fwd", "rlsde_rollout_bwd", "rlsde_reduce_stats",
     "rlsde_tables", "rlsde_tables_colsum", "rlsde_env_step", "rlsde_noise_fill",
-    "rlsde_dp_scratch_bytes", "rlsde_dp_sweep", "rlsde_dp_rowmax", "rlsde_rollout_transitions",
+    "rlsde_dp_scratch_bytes", "rlsde_dp_sweep", "rlsde_dp_rowmax", "rlsde_rollout_transitions", "rlsde_launch_count",
 ]
 
 
@@ -85,6 +85,7 @@ def load():
     lib.rlsde_strerror.restype = C.c_char_p
     lib.rlsde_strerror.argtypes = [C.c_int]
     lib.rlsde_last_cuda_error.restype = C.c_char_p
+    lib.rlsde_launch_count.restype = C.c_longlong
     lib.rlsde_device_info.argtypes = [C.POINTER(i32)] * 3
     lib.rlsde_supported.argtypes = [i32, i32, i32]
     lib.rlsde_param_count.restype = i64

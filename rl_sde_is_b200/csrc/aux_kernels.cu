@@ -76,6 +76,7 @@ int launch_reduce_stats(long long K, long long n_steps_lim, bool f64, const void
   if (f64) stats_partial_kernel<true><<<nb, 256, 0, stream>>>(K, n_steps_lim, G, S, T, l2, logw, partial);
   else stats_partial_kernel<false><<<nb, 256, 0, stream>>>(K, n_steps_lim, G, S, T, l2, logw, partial);
   stats_final_kernel<<<1, 32, 0, stream>>>(nb, partial, stats);
+  note_kernel_launches(2);
   return (int)cudaGetLastError();
 }
 
@@ -116,6 +117,7 @@ int launch_noise_fill(unsigned long long seed, long long traj_offset, long long 
   if (nb > 148 * 16) nb = 148 * 16;
   const float scale2 = (float)(-2.0 * dt * 0.6931471805599453);
   noise_fill_kernel<<<(unsigned)nb, 256, 0, stream>>>(seed, traj_offset, K, d, pass_begin, n_pass, scale2, out);
+  note_kernel_launches(1);
   return (int)cudaGetLastError();
 }
 
@@ -202,6 +204,7 @@ int launch_env_step(const StepArgs& A, bool f64, cudaStream_t stream) {
   const unsigned nb = (unsigned)((A.K + 127) / 128);
   if (f64) env_step_kernel<true><<<nb, 128, 0, stream>>>(A);
   else env_step_kernel<false><<<nb, 128, 0, stream>>>(A);
+  note_kernel_launches(1);
   return (int)cudaGetLastError();
 }
 

@@ -2,6 +2,7 @@
 // precomputation of the environment constants the way torch / numpy round them, dispatch on the
 // policy shape, and stream-ordered launches.  No torch types, no exceptions, no global mutable state
 // except the thread-local text of the last CUDA error.
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -14,6 +15,8 @@
 namespace rlsde {
 
 static thread_local char g_last_cuda_error[256] = "";
+static std::atomic<long long> g_kernel_launches{0};
+void note_kernel_launches(int n) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static int cuda_fail(cudaError_t e, const char* where) {
   snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", where, cudaGetErrorString(e));
@@ -118,6 +121,8 @@ const char* rlsde_strerror(int status) {
 }
 
 const char* rlsde_last_cuda_error(void) { return g_last_cuda_error; }
+
+long long rlsde_launch_count(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
 
 int rlsde_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
   int dev = 0;

@@ -17,6 +17,9 @@ namespace rlsde {
 
 typedef unsigned long long u64;
 
+// diagnostics: every launcher reports the kernels it enqueued (rlsde_launch_count in the C ABI)
+void note_kernel_launches(int n);
+
 // ------------------------------------------------------------------ packed fp32 helpers
 __device__ __forceinline__ u64 pack2(float lo, float hi) {
   u64 r;

@@ -168,6 +168,7 @@ int launch_dp_sweep(const double* P, long long Ns, long long Na, const double* R
   else dp_sweep_partial_kernel<false><<<grid, SWEEP_THREADS, 0, stream>>>(P, Ns, cols, v, rows, scratch);
   dp_sweep_epilogue_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, stream>>>(scratch, n_split, odd ? 2 : 1, Ns, Na, R, in_ts,
                                                                                 gamma, values);
+  note_kernel_launches(2);
   return (int)cudaGetLastError();
 }
 
@@ -175,6 +176,7 @@ size_t dp_sweep_scratch_bytes(long long Ns, long long Na) { return (size_t)SWEEP
 
 int launch_dp_rowmax(const double* values, long long Ns, long long Na, double* vmax, long long* arg, cudaStream_t stream) {
   dp_rowmax_kernel<<<(unsigned)((Ns + 7) / 8), 256, 0, stream>>>(values, Ns, Na, vmax, arg);
+  note_kernel_launches(1);
   return (int)cudaGetLastError();
 }
 

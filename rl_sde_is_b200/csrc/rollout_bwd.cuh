@@ -124,14 +124,16 @@ __device__ __forceinline__ void em_step_f32(const FwdArgs& A, float (&x)[D], con
   }
 }
 
-// Resident blocks per SM the register allocation aims for (measured on B200, d = 1, H = 32: see DESIGN.md)
+// Resident blocks per SM the register allocation aims for.  Measured on B200 (K = 4e5 / 2e5, tools/bench_train.py):
+//   d = 1:  2 blocks (210 registers) 63.3 ms, 3 blocks (168) 61.4 ms, 4 blocks (128, 16 B of spills) 58.2 ms
+//   d = 10: 2 blocks 22.4 ms, 3 blocks 27.4 ms, 4 blocks 29.8 ms (the wider head spills)
 #ifndef RLSDE_BWD_MIN_BLOCKS
-#define RLSDE_BWD_MIN_BLOCKS 2
+#define RLSDE_BWD_MIN_BLOCKS(D) ((D) == 1 ? 4 : 2)
 #endif
 
 // Per-warp partial gradient layout = state_dict order: W1 (H,D), b1 (H), W2 (H,H), b2 (H), W3 (D,H), b3 (D)
 template <int D, int H, bool FAST>
-__global__ void __launch_bounds__(128, RLSDE_BWD_MIN_BLOCKS) rollout_bwd_kernel(const __grid_constant__ MlpConst<D, H> W,
+__global__ void __launch_bounds__(128, RLSDE_BWD_MIN_BLOCKS(D)) rollout_bwd_kernel(const __grid_constant__ MlpConst<D, H> W,
                                                           const __grid_constant__ FwdArgs A, float* __restrict__ partial) {
   static_assert(H == 32 || H == 64, "column-per-lane accumulation needs H in {32, 64}");
   constexpr int CPL = H / 32;                 // columns of the HxH block owned by a lane

@@ -46,6 +46,7 @@ static int launch_bwd_variant(const float* params_host, const FwdArgs& args, flo
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   bwd_reduce_kernel<<<(P + 127) / 128, 128, 0, stream>>>(partial, (int)n_warps, P, scale, grad);
+  note_kernel_launches(2);
   return (int)cudaGetLastError();
 }
 

@@ -40,6 +40,7 @@ static int launch_fwd_variant(const float* params_host, const FwdArgs& args, int
   a.counter = args.ws_work_counters;
   if (!compact) {
     kern<<<(unsigned)grid, block, 0, stream>>>(W, a);
+    note_kernel_launches(1);
     return (int)cudaGetLastError();
   }
   // ---- tail compaction.  The main launch stops DRAIN iterations after the work counter runs dry: its live
@@ -74,6 +75,7 @@ static int launch_fwd_variant(const float* params_host, const FwdArgs& args, int
   f.cont_out = nullptr; f.cont_count_out = nullptr;
   f.round_steps = 0xffffffffu; f.drain_steps = 0xffffffffu;
   kern<<<(unsigned)grid, block, 0, stream>>>(W, f);
+  note_kernel_launches(r + 2);          // main launch + r resume rounds + the run-to-completion launch
   return (int)cudaGetLastError();
 }
 

@@ -17,6 +17,7 @@ static int launch_fwd_warp_variant(const float* params_host, const FwdArgs& args
   MlpConst<D, WARP_H> W;
   pack_mlp_const<D, WARP_H>(params_host, FAST, W);
   rollout_fwd_warp_kernel<D, F64, FAST><<<(unsigned)warp_grid(args.K, sm_count), 128, 0, stream>>>(W, args);
+  note_kernel_launches(1);
   return (int)cudaGetLastError();
 }
 
@@ -40,6 +41,7 @@ static int launch_bwd_warp_variant(const float* params_host, const FwdArgs& args
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   bwd_reduce_kernel<<<(P + 127) / 128, 128, 0, stream>>>(partial, (int)(grid * 4), P, scale, grad);
+  note_kernel_launches(2);
   return (int)cudaGetLastError();
 }
 

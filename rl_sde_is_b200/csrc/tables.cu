@@ -193,15 +193,18 @@ int launch_tables(const double* state_grid, long long Ns, const double* action_g
     dim3 grid((unsigned)((cols + 127) / 128), (unsigned)n_chunks);
     tables_gl_kernel<<<grid, 128, 0, stream>>>(state_grid, Ns, action_grid, Na, in_ts, n_ts > 0 ? 1.0 / (double)n_ts : 0.0,
                                                alpha, sigma, dt, h_half, sprime_begin, sprime_end, P);
+    note_kernel_launches(1);
   } else if (P && sprime_end > sprime_begin) {
     const long long nsp = sprime_end - sprime_begin;
     dim3 grid((unsigned)((Na + 127) / 128), (unsigned)Ns, (unsigned)((nsp + TABLE_TILE - 1) / TABLE_TILE));
     tables_kernel<<<grid, 128, 0, stream>>>(state_grid, Ns, action_grid, Na, in_ts, n_ts > 0 ? 1.0 / (double)n_ts : 0.0,
                                             alpha, sigma, dt, h_half, sprime_begin, sprime_end, P);
+    note_kernel_launches(1);
   }
   if (R) {
     const long long n = Ns * Na;
     rtable_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(Ns, action_grid, Na, in_ts, dt, R);
+    note_kernel_launches(1);
   }
   return (int)cudaGetLastError();
 }
@@ -219,6 +222,7 @@ int launch_tables_colsum(const double* P, long long n_sprime, long long Ns, long
                          cudaStream_t stream) {
   const long long cols = Ns * Na;
   colsum_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, stream>>>(P, n_sprime, cols, colsum);
+  note_kernel_launches(1);
   return (int)cudaGetLastError();
 }
 

@@ -67,6 +67,42 @@ def sample_loss_vectorized(env, model, K, *, noise=None, seed=None, n_steps_lim=
     return loss, out.G.cpu().numpy(), (T + 1).astype(np.float64)
 
 
+def _loss_and_grads_fused(env, model, K, *, noise=None, seed=None, n_steps_lim=10**6, tanh="precise", stoch_int="reference",
+                          ckpt_every=None, device=None, kernel="auto"):
+    """What ``sample_loss_vectorized`` + ``eff_loss.backward()`` produce, with one host synchronisation and without the
+    autograd graph: sets ``p.grad`` of the policy's parameters and returns ``(loss float, return_fht, time_steps)``.
+    Used by ``reinforce()``; results are those of the autograd route (same kernels, same arguments)."""
+    d, H = R.policy_shape(model)
+    if d != env.d:
+        raise L.RlsdeError(f"policy dimension {d} != env.d {env.d}")
+    env_c = R.env_struct(env, L.HIT_ALL_GE_LB)
+    mlp_c = L.make_mlp(d, H)
+    dev = R._cuda_device(device)
+    if noise is not None:
+        noise = torch.as_tensor(np.ascontiguousarray(noise, dtype=np.float32)) if not torch.is_tensor(noise) else noise
+        noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+    lim = int(n_steps_lim) if noise is None else min(int(n_steps_lim), int(noise.shape[0]))
+    if ckpt_every is None:
+        ckpt_every = R.choose_ckpt_every(int(K), d, lim)
+    linears = R.policy_linears(model)
+    with torch.no_grad():
+        params_host = torch.cat([t.reshape(-1) for lin in linears for t in (lin.weight, lin.bias)]).to(torch.float32).numpy()
+    stats, grad, G, T = R.rollout_loss_and_grad(env_c, mlp_c, params_host, int(K), seed=_next_seed(seed), n_steps_lim=n_steps_lim,
+                                                noise=noise, tanh=tanh, stoch_int=stoch_int, ckpt_every=ckpt_every,
+                                                device=dev, kernel=kernel)
+    if (T < 0).any():
+        raise L.RlsdeError(f"{int((T < 0).sum())} of {K} trajectories did not reach the target set within "
+                           f"{lim} passes; raise n_steps_lim")
+    g = torch.from_numpy(grad.copy())
+    off = 0
+    for lin in linears:
+        for t in (lin.weight, lin.bias):
+            piece = g[off:off + t.numel()].view_as(t).to(t.dtype)
+            t.grad = piece if t.grad is None else t.grad + piece
+            off += t.numel()
+    return float(np.float32(stats[L.ST_SUM_LOSS] / K)), G.copy(), (T + 1).astype(np.float64)
+
+
 class _LossWithAux(torch.autograd.Function):
     """eff_loss = mean_k(-G_k - sg(G_k) S_k) as a differentiable function of the flat policy parameters: forward launches
     the rollout kernel (with state checkpoints), backward the reverse kernel -- what autograd does in the reference over
@@ -128,7 +164,11 @@ def reinforce(env, gamma=1., d_hidden_layer=256, n_layers=3, batch_size=1000, lr
     hidden = [d_hidden_layer] * (n_layers - 1)
     model = DeterministicPolicy(state_dim=env.state_space_dim, action_dim=env.action_space_dim,
                                 hidden_sizes=hidden, activation=nn.Tanh())
-    optimizer = optim.Adam(model.parameters(), lr=lr)
+    try:
+        optimizer = optim.Adam(model.parameters(), lr=lr, fused=True)     # one pass over the 6 small tensors (same update rule)
+    except (TypeError, RuntimeError, ValueError):
+        optimizer = optim.Adam(model.parameters(), lr=lr)
+    fused_path = rollout_opts.get("dist") is None and all(p.device.type == "cpu" for p in model.parameters())
     data = dict(gamma=gamma, n_layers=n_layers, d_hidden_layer=d_hidden_layer, batch_size=batch_size, lr=lr,
                 n_iterations=n_iterations, seed=seed, backup_freq_iterations=backup_freq_iterations, model=model)
     if load:
@@ -170,14 +210,17 @@ def reinforce(env, gamma=1., d_hidden_layer=256, n_layers=3, batch_size=1000, lr
         if not load:
             t0 = time.time()
             optimizer.zero_grad()
-            eff_loss, batch_returns, batch_time_steps = sample_loss_vectorized(env, model, batch_size, **rollout_opts)
-            eff_loss.backward()
+            if fused_path:     # same kernels as sample_loss_vectorized + backward(), one host synchronisation
+                eff_loss, batch_returns, batch_time_steps = _loss_and_grads_fused(env, model, batch_size, **rollout_opts)
+            else:
+                eff_loss, batch_returns, batch_time_steps = sample_loss_vectorized(env, model, batch_size, **rollout_opts)
+                eff_loss.backward()
             optimizer.step()
             cts[i] = time.time() - t0          # wall clock of zero_grad -> loss -> backward -> step, like the reference's ct
 
             returns = np.append(returns, batch_returns)
             time_steps = np.append(time_steps, batch_time_steps)
-            losses[i] = float(eff_loss.detach())
+            losses[i] = float(eff_loss.detach()) if torch.is_tensor(eff_loss) else eff_loss
             exp_returns[i] = np.mean(batch_returns)
             var_returns[i] = np.var(batch_returns)
             exp_time_steps[i] = np.mean(batch_time_steps)

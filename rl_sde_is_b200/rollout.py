@@ -257,6 +257,67 @@ def rollout_backward(env_c, mlp_c, params_host, fwd: RolloutOut, loss_scale, *, 
     return grad
 
 
+def rollout_loss_and_grad(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=10**6, noise=None, tanh="precise",
+                          stoch_int="reference", ckpt_every=1, device=None, kernel="auto", balance=True):
+    """One REINFORCE evaluation with a single host synchronisation: K1 (with checkpoints), the statistics reduction and
+    K2 are enqueued back to back, and loss numerator, gradient, returns and hit indices come back in ONE device-to-host
+    copy.  (The autograd route -- sample_loss_vectorized + .backward() -- synchronises after each kernel; at the
+    reference's K = 100 those round trips cost as much as the kernels.)
+
+    Returns ``(stats float64[RLSDE_NSTATS], grad float32[P] of mean_k(-G_k - sg(G_k) S_k), G float32[K], T int32[K])``
+    as NumPy arrays."""
+    lib = L.load()
+    dev = _cuda_device(device)
+    K = int(K)
+    P = int(lib.rlsde_param_count(mlp_c))
+    params_host = np.ascontiguousarray(params_host, dtype=np.float32)
+    align = lambda n: (n + 15) & ~15
+    o_stats, o_grad = 0, 128
+    o_G = o_grad + align(4 * P)
+    o_T = o_G + align(4 * K)
+    pack = torch.empty(o_T + align(4 * K), dtype=torch.uint8, device=dev)
+    pack[:128].zero_()
+    stats = pack[o_stats:o_stats + 128].view(torch.float64)
+    grad = pack[o_grad:o_grad + 4 * P].view(torch.float32)
+    G = pack[o_G:o_G + 4 * K].view(torch.float32)
+    T = pack[o_T:o_T + 4 * K].view(torch.int32)
+    S = torch.empty(K, dtype=torch.float32, device=dev)
+    flags = L.F_STORE_PATH
+    cfg = L.RlsdeRolloutCfg()
+    cfg.K, cfg.traj_offset, cfg.K_global = K, 0, K
+    cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    cfg.n_steps_lim = int(n_steps_lim)
+    if noise is not None:
+        if noise.device != dev or noise.dtype != torch.float32 or not noise.is_contiguous() or noise.dim() != 3 \
+                or noise.shape[1] != K or noise.shape[2] != env_c.d:
+            raise L.RlsdeError(f"noise must be a contiguous float32 CUDA tensor [n_steps, {K}, {env_c.d}]")
+        flags |= L.F_NOISE_INJECTED
+        cfg.noise_steps = int(noise.shape[0])
+    flags |= {"precise": 0, "fast": L.F_TANH_FAST}[tanh]
+    flags |= {"reference": 0, "exact": L.F_STOCH_INT_EXACT}[stoch_int]
+    flags |= {"auto": 0, "thread": L.F_KERNEL_THREAD, "warp": L.F_KERNEL_WARP}[kernel]
+    lim_eff = min(cfg.n_steps_lim, cfg.noise_steps) if noise is not None else cfg.n_steps_lim
+    cfg.ckpt_every = int(ckpt_every)
+    cfg.ckpt_stride = (lim_eff + cfg.ckpt_every - 1) // cfg.ckpt_every
+    cfg.flags = flags
+    path = torch.empty((K, cfg.ckpt_stride, env_c.d), dtype=torch.float32, device=dev)
+    ws = _workspace(dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.rlsde_rollout_fwd(env_c, mlp_c, params_host.ctypes.data, cfg, _ptr(noise), 0, _ptr(G), _ptr(S), _ptr(T), 0, 0,
+                                   _ptr(path), _ptr(stats), _ptr(ws), ws.numel(), stream)
+        L.check(rc, "rlsde_rollout_fwd")
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        thread_path = (flags & L.F_KERNEL_THREAD) or not ((flags & L.F_KERNEL_WARP) or K <= 16 * n_sm)
+        order = torch.argsort(T, descending=True, stable=True) if balance and thread_path and K > 32 else None
+        rc = lib.rlsde_rollout_bwd(env_c, mlp_c, params_host.ctypes.data, cfg, _ptr(noise), _ptr(G), _ptr(T), _ptr(path),
+                                   _ptr(order), 1.0 / K, _ptr(grad), _ptr(ws), ws.numel(), stream)
+        L.check(rc, "rlsde_rollout_bwd")
+    host = pack.cpu().numpy()                               # the iteration's only synchronisation
+    return (host[o_stats:o_stats + 128].view(np.float64), host[o_grad:o_grad + 4 * P].view(np.float32),
+            host[o_G:o_G + 4 * K].view(np.float32), host[o_T:o_T + 4 * K].view(np.int32))
+
+
 def choose_ckpt_every(K, d, n_steps_lim, budget_bytes=8 << 30):
     """Smallest checkpoint spacing whose path store fits the budget (1 = keep every state)."""
     for c in (1, 2, 4, 8, 16, 32):

@@ -538,3 +538,35 @@ def test_reinforce_writes_and_loads_reference_layout(tmp_path):
     assert type(back["model"]).__name__ == "DeterministicPolicy"
     again = reinforce(env, load=True, test=True, test_batch_size=64, test_freq_iterations=2, policy_opt=policy_opt, **kw)
     assert again["test_mean_returns"].shape == (3,) and np.array_equal(again["losses"], data["losses"])
+
+
+@pytest.mark.parametrize("fixture,prefix", [("rollout_torch_1d", "a_"), ("rollout_torch_2d", "a_")])
+def test_fused_training_step_equals_autograd_route(golden, fixture, prefix):
+    """reinforce()'s single-synchronisation step (K1 + K2 enqueued back to back, one device-to-host copy) gives exactly
+    what sample_loss_vectorized + backward() give: same kernels, same arguments."""
+    from rl_sde_is_b200.reinforce_deterministic_core import _loss_and_grads_fused, sample_loss_vectorized
+    g = golden(fixture)
+    d, alpha, beta, dt = _env(g, prefix)
+    env = _make_env(d, alpha, beta, dt)
+    K = g[prefix + "noise"].shape[1]
+    m1, m2 = _model_from(g, prefix, d), _model_from(g, prefix, d)
+    loss1, ret1, steps1 = sample_loss_vectorized(env, m1, K, noise=g[prefix + "noise"])
+    loss1.backward()
+    loss2, ret2, steps2 = _loss_and_grads_fused(env, m2, K, noise=g[prefix + "noise"])
+    assert float(loss1.detach()) == loss2 and np.array_equal(ret1, ret2) and np.array_equal(steps1, steps2)
+    for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.equal(p1.grad, p2.grad), k
+    np.testing.assert_allclose(loss2, float(g[prefix + "loss"]), rtol=2e-5)
+    # in-kernel RNG, larger batch (thread-per-trajectory kernels, length-sorted reverse pass)
+    torch.manual_seed(5)
+    from rl_sde_is_b200.models import DeterministicPolicy
+    ma = DeterministicPolicy(d, d, [32, 32], nn.Tanh())
+    ma.policy[4].bias.data.fill_(1.5)
+    mb = DeterministicPolicy(d, d, [32, 32], nn.Tanh())
+    mb.load_state_dict(ma.state_dict())
+    la, ra, sa = sample_loss_vectorized(env, ma, 6000, seed=9, n_steps_lim=20000)
+    la.backward()
+    lb, rb, sb = _loss_and_grads_fused(env, mb, 6000, seed=9, n_steps_lim=20000)
+    assert float(la.detach()) == lb and np.array_equal(ra, rb) and np.array_equal(sa, sb)
+    for (k, p1), (_, p2) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert torch.equal(p1.grad, p2.grad), k
