@@ -267,11 +267,12 @@ def run_gpu_arm(args):
     per_gpu_steps = useful / n_gpus / (dev_ms * 1e-3)
     achieved = per_gpu_steps * FLOP_PER_STEP / 1e12
     roofline = {"bound": "fp32_cuda_core", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                "frac": achieved / peak_tflops, "traffic": 1.61e6, "traffic_unit": "bytes per launch (dram read + write, ncu --set full, profiles/r01)",
+                "frac": achieved / peak_tflops, "traffic": 2.199e9, "traffic_unit": "bytes per launch (dram read + write, ncu --set full, profiles/r01/ncu_rollout_fwd_v2.txt): "
+                                                   "the continuation records of the time-sliced schedule, 24 B per 8 passes; 86 GB/s",
                 "note": f"peak = {sm} SMs x 128 FMA lanes x 2 x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json; FFMA "
                         f"microbenchmark in profiles/ confirms 128 lanes/clk/SM); algorithmic work {FLOP_PER_STEP} FLOP per useful "
                         "trajectory-step (SURVEY 8d), timed per launch with CUDA events incl. the statistics reduction; the "
-                        "kernel keeps its state in registers, HBM traffic is ~16 B per trajectory"}
+                        "kernel keeps its state in registers (results: 16 B per trajectory)"}
 
     extra = {"is_mean": summ.get("is_mean"), "is_rel_error": summ.get("is_rel_error"), "mean_return": summ.get("mean_return"),
              "frac_unfinished": summ["n_unfinished"] / max(summ["n"], 1), "useful_steps_per_step": useful / args.steps,

@@ -92,13 +92,13 @@ static int fill_cfg(const rlsde_rollout_cfg* cfg, FwdArgs& A) {
   return RLSDE_OK;
 }
 
-// workspace layout: [0, 1024) counters (32 x u64 work counters, then 64 x u32 continuation counts);
-// statistics partials; two buffers of continuation records (tail compaction); reverse-pass partials
+// workspace layout: [0, 1024) counters (u64: items claimed, records queued, trajectories completed); statistics partials;
+// reverse-pass partials; then, to the end of the buffer, the ring of continuation records of the time-sliced forward
+// rollout (one record per trajectory + one per lane: rlsde_workspace_bytes(K) sizes it for the largest record)
 constexpr size_t WS_COUNTER_BYTES = 1024;
 constexpr size_t WS_STATS_BYTES = (size_t)STATS_BLOCKS * RLSDE_NSTATS * sizeof(double);
-constexpr long long WS_CONT_CAPACITY = 148LL * 16 * 128;                      // lanes of the largest forward grid
+constexpr long long WS_MAX_LANES = 148LL * 16 * 128;                          // lanes of the largest forward grid
 constexpr size_t WS_CONT_REC_BYTES = 16 + 8 * (RLSDE_MAX_D + 3);              // >= sizeof(ContRec<D, F64>) for every D
-constexpr size_t WS_CONT_BYTES = 2 * (size_t)WS_CONT_CAPACITY * WS_CONT_REC_BYTES;
 
 }  // namespace rlsde
 
@@ -149,9 +149,13 @@ int64_t rlsde_param_count(const rlsde_mlp* mlp) {
   return d * H + H + (int64_t)(mlp->n_hidden - 1) * (H * H + H) + H * o + o;
 }
 
+static size_t ws_fixed_bytes() { return WS_COUNTER_BYTES + WS_STATS_BYTES + bwd_workspace_bytes(); }
+
 size_t rlsde_workspace_bytes(int64_t K) {
-  (void)K;
-  return WS_COUNTER_BYTES + WS_STATS_BYTES + WS_CONT_BYTES + bwd_workspace_bytes();
+  const long long k = K > 0 ? K : 0;
+  long long cap = 1;
+  while (cap < k + WS_MAX_LANES) cap <<= 1;             // the ring's capacity is a power of two
+  return ws_fixed_bytes() + (size_t)cap * WS_CONT_REC_BYTES;
 }
 
 // transition-stream outputs of a forward rollout (all null = none)
@@ -187,12 +191,10 @@ static int rollout_fwd_impl(const rlsde_env* env, const rlsde_mlp* mlp, const fl
   A.tr_next = tr.next_state; A.tr_done = tr.done;
   if (tr.base) A.flags = (A.flags & ~RLSDE_F_KERNEL_WARP) | RLSDE_F_KERNEL_THREAD;   // the stream lives in the throughput kernel
   A.counter = (unsigned long long*)workspace_dev;
-  A.ws_work_counters = (unsigned long long*)workspace_dev;
-  A.ws_cont_counts = (unsigned*)((char*)workspace_dev + 256);
-  if (workspace_bytes >= WS_COUNTER_BYTES + WS_STATS_BYTES + WS_CONT_BYTES) {
-    A.ws_cont_buf[0] = (unsigned char*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES;
-    A.ws_cont_buf[1] = A.ws_cont_buf[0] + (size_t)WS_CONT_CAPACITY * WS_CONT_REC_BYTES;
-    A.ws_cont_capacity = WS_CONT_CAPACITY;
+  A.q_ctrl = (unsigned long long*)workspace_dev;
+  if (workspace_bytes > ws_fixed_bytes()) {             // ring of continuation records: whatever lies behind the fixed part
+    A.q_ring = (unsigned char*)workspace_dev + ws_fixed_bytes();
+    A.q_cap = (long long)(workspace_bytes - ws_fixed_bytes());      // bytes; the launcher turns it into a record count
   }
   if (A.K == 0) return RLSDE_OK;
   int sm = 0;
@@ -246,7 +248,7 @@ int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
   int rc = check_env_mlp(env, mlp);
   if (rc != RLSDE_OK) return rc;
   if (!params_host || !G_dev || !T_dev || !path_dev || !grad_dev || !workspace_dev) return RLSDE_ERR_INVALID_ARG;
-  if (workspace_bytes < rlsde_workspace_bytes(cfg ? cfg->K : 0)) return RLSDE_ERR_WORKSPACE;
+  if (workspace_bytes < ws_fixed_bytes()) return RLSDE_ERR_WORKSPACE;
   FwdArgs A;
   memset(&A, 0, sizeof(A));
   fill_env(env, A);
@@ -262,7 +264,7 @@ int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
   if ((rc = device_sm_count(&sm)) != RLSDE_OK) return rc;
   cudaError_t e = cudaMemsetAsync(workspace_dev, 0, WS_COUNTER_BYTES, stream);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
-  float* partial = (float*)((char*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES + WS_CONT_BYTES);
+  float* partial = (float*)((char*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES);
   int lrc = -1;
   const bool warp_path = use_warp_kernels(A, mlp->d_hidden, sm, true);
 #define X(D_, H_)                                                                                                          \

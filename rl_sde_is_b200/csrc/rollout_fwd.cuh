@@ -14,9 +14,23 @@
 // (f32) or numpy's (f64, RLSDE_F_STATE_F64) results.
 //
 // Scheduling: a warp's 32 lanes run 32 independent trajectories in lock step.  A lane whose
-// trajectory retires takes the next global trajectory id (warp-aggregated atomicAdd) at the next
-// noise-block boundary, so lanes stay busy until the work runs out; the warp leaves the loop when a
-// ballot shows no live lane (first-hitting-time divergence only costs the tail).
+// trajectory retires takes the next work item (warp-aggregated atomicAdd) at the next noise-block
+// boundary, so lanes stay busy until the work runs out.
+//
+// Time slicing.  Trajectory lengths are unknown in advance and bounded only by n_steps_lim, so with
+// run-to-completion scheduling the launch ends with a tail of (longest trajectory) x (time of a pass): the
+// last-started long trajectory runs on an otherwise empty GPU (measured: 4.3 ms of a 27.5 ms launch at
+// 1e6 trajectories, whatever the batch size).  Instead a trajectory runs for at most `q_quantum` passes
+// per slice; a lane whose slice is over appends the trajectory's state (24 B at d = 1) to a FIFO in
+// global memory and takes the next item.  Items are served in order -- first all fresh trajectories,
+// then their continuations in the order they were queued -- which makes the schedule breadth-first: all
+// trajectories advance together and the tail shrinks to a few quanta.  (Warps do not advance at the same pace -- with
+// eight warps per scheduler some execute 8 000 passes while others execute 700 in the same launch -- so the last
+// slice of a trajectory that sits in a starved warp is what ends the launch: short slices, 8 passes at n_steps_lim =
+// 1000, measured best; they cost ~3 % in steady state.)  The FIFO is a ring of records with
+// a sequence word per slot (producer: write, fence, publish epoch; consumer: claim an index, poll its
+// slot between passes, never blocking the warp's other lanes); the launch ends when every trajectory has
+// reported completion.  Per-trajectory arithmetic does not depend on the slicing: results are bit-identical.
 #pragma once
 #include "common.cuh"
 #include "../../include/rlsde.h"
@@ -64,20 +78,12 @@ struct FwdArgs {
   float* tr_reward;              // [n]
   float* tr_next;                // [n][d]  state after the pass (also computed on the pass that detects the hit)
   unsigned char* tr_done;        // [n]
-  // ---- resumable rollouts (tail compaction, see rollout_fwd_inst.cuh).  A launch draws work items from
-  //      [continuation records | fresh trajectories]; when its step budget ends, live lanes dump a record.
-  const unsigned char* cont_in;        // records to resume, or nullptr
-  const unsigned* cont_count_in;       // device-side number of records in cont_in
-  unsigned char* cont_out;             // where live lanes dump their state at the deadline, or nullptr (run to completion)
-  unsigned* cont_count_out;
-  long long K_fresh;                   // fresh trajectories started by this launch (ids [0, K_fresh))
-  unsigned round_steps;                // warp iterations after which live lanes dump (0xffffffff: never)
-  unsigned drain_steps;                // iterations a warp keeps going once the work counter is seen exhausted
-  // scratch handed in by the C ABI (caller's workspace)
-  unsigned long long* ws_work_counters;
-  unsigned* ws_cont_counts;
-  unsigned char* ws_cont_buf[2];
-  long long ws_cont_capacity;          // records per buffer
+  // ---- time-sliced scheduling (see the header comment).  q_ring == nullptr: every trajectory runs to completion.
+  unsigned char* q_ring;               // ring of ContRec<D, F64> records, all-zero at launch
+  long long q_cap;                     // records in the ring: a power of two >= K + lanes of the grid
+  int q_cap_log2;
+  unsigned long long* q_ctrl;          // [0] items claimed (== counter), [1] continuation records queued, [2] trajectories completed
+  int q_quantum;                       // passes per slice
 };
 
 // State of an in-flight trajectory: everything a lane needs to continue it (x, accumulators, pass index).
@@ -85,7 +91,7 @@ template <int D, bool F64>
 struct alignas(8) ContRec {
   long long traj;
   int k;
-  int pad;
+  int seq;            // 0: never used; e > 0: holds the e-th record of this slot; -e: that record has been taken
   typename RealT<F64>::type x[D];
   typename RealT<F64>::type G, S, L2;
 };
@@ -95,6 +101,28 @@ __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 
+// Cold path of the FIFO: a producer found its slot still holding an unread record (the ring is larger than the number of
+// records in flight, so this needs a reader stalled for a whole lap).  Kept out of line: inlined, the spin loop costs the
+// rollout kernel ~15 registers.
+static __device__ __noinline__ void wait_for_slot(volatile int* seq, int free_mark) {
+  while (*seq != free_mark) __nanosleep(64);
+}
+
+// A warp without a live lane parks here until the record one of its lanes waits for has been published, or every
+// trajectory has completed.  Out of line and with exponential back-off: towards the end of a launch most warps are in
+// this state, and a tight poll loop (the whole refill block every 200 ns) took the issue slots the last working warps
+// needed (measured: the end of the launch stretched from ~0.4 ms to 2-4 ms).
+static __device__ __noinline__ void park_idle_warp(volatile int* seq, int epoch, bool pending,
+                                                   const volatile unsigned long long* completed, unsigned long long K) {
+  unsigned ns = 128;
+  for (;;) {
+    const bool wake = (pending && *seq == epoch) || *completed >= K;
+    if (__any_sync(0xffffffffu, wake)) return;
+    __nanosleep(ns);
+    if (ns < 4096) ns <<= 1;
+  }
+}
+
 template <int D>
 struct NoisePlan {
   // passes served by one Philox block (D = 1, 2) or blocks needed per pass (D >= 3)
@@ -103,8 +131,10 @@ struct NoisePlan {
   static constexpr int NZ = 4 * BPP;
 };
 
+// d = 1 is held to 64 registers (8 blocks per SM: ptxas finds a spill-free allocation under the bound, but settles at
+// 67 without it); the wider shapes would spill under the same bound and are left to the default heuristics.
 template <int D, int H, bool F64, bool FAST>
-__global__ void __launch_bounds__(128) rollout_fwd_kernel(const __grid_constant__ MlpConst<D, H> W,
+__global__ void __launch_bounds__(128, (D == 1 ? 8 : 1)) rollout_fwd_kernel(const __grid_constant__ MlpConst<D, H> W,
                                                           const __grid_constant__ FwdArgs A) {
   typedef typename RealT<F64>::type real;
   constexpr int SPB = NoisePlan<D>::SPB;
@@ -118,11 +148,13 @@ __global__ void __launch_bounds__(128) rollout_fwd_kernel(const __grid_constant_
   const bool want_l2 = (D == 1) && A.policy_opt != nullptr && A.l2 != nullptr;
   const long long lim = inject ? (A.noise_steps < A.n_steps_lim ? A.noise_steps : A.n_steps_lim) : A.n_steps_lim;
   typedef ContRec<D, F64> Rec;
-  const long long n_cont = A.cont_count_in ? (long long)*A.cont_count_in : 0;
-  const long long n_work = n_cont + A.K_fresh;
-  unsigned deadline = A.round_steps;
+  const bool sliced = A.q_ring != nullptr;
+  Rec* const ring = reinterpret_cast<Rec*>(A.q_ring);
+  // live state is kept small (the register budget of 8 blocks per SM is 64): while a lane waits for a record, `traj`
+  // holds the record's index; slices end where the pass index is a multiple of the quantum (a power of two)
+  const int qmask = A.q_quantum - 1;
 
-  bool alive = false, exhausted = false;
+  bool alive = false, exhausted = false, pending = false, fin = false;
   long long traj = 0;
   int k = 0, ck = 0;
   real x[D];
@@ -135,61 +167,86 @@ __global__ void __launch_bounds__(128) rollout_fwd_kernel(const __grid_constant_
 
   for (unsigned it = 0;; ++it) {
     if ((it & (SPB - 1)) == 0) {
-      if (A.cont_out != nullptr) {
-        // every 16 iterations: has the launch run out of work items?  then finish this round soon, so that the
-        // survivors can be re-packed into dense warps by the next launch
-        if ((it & 15u) == 0 && deadline == A.round_steps) {
-          unsigned long long c = 0;
-          if (lane == 0) c = *reinterpret_cast<volatile unsigned long long*>(A.counter);
-          c = __shfl_sync(FULL, c, 0);
-          if ((long long)c >= n_work && A.drain_steps != 0xffffffffu) {
-            const unsigned dl = it + A.drain_steps;
-            deadline = dl < deadline ? dl : deadline;
-          }
+      if (sliced) {
+        // (a) report the trajectories that completed since the last boundary
+        const unsigned fm = __ballot_sync(FULL, fin);
+        if (fm) {
+          if (lane == __ffs(fm) - 1) atomicAdd(A.q_ctrl + 2, (unsigned long long)__popc(fm));
+          fin = false;
         }
-        if (it >= deadline) {
-          const unsigned live = __ballot_sync(FULL, alive);
-          if (live) {
-            unsigned base = 0;
-            const int leader = __ffs(live) - 1;
-            if (lane == leader) base = atomicAdd(A.cont_count_out, (unsigned)__popc(live));
-            base = __shfl_sync(FULL, base, leader);
-            if (alive) {
-              Rec* r = reinterpret_cast<Rec*>(A.cont_out) + (base + __popc(live & ((1u << lane) - 1u)));
-              r->traj = traj; r->k = k; r->pad = 0; r->G = G; r->S = S; r->L2 = L2;
+        // (b) slice over: append the trajectory to the FIFO
+        const bool expire = alive && k != 0 && (k & qmask) == 0;   // (a resumed lane is past this check: it resumes in (d))
+        const unsigned em = __ballot_sync(FULL, expire);
+        if (em) {
+          unsigned long long base = 0;
+          const int leader = __ffs(em) - 1;
+          if (lane == leader) base = atomicAdd(A.q_ctrl + 1, (unsigned long long)__popc(em));
+          base = __shfl_sync(FULL, base, leader);
+          if (expire) {
+            const unsigned long long j = base + __popc(em & ((1u << lane) - 1u));
+            Rec* r = ring + (long long)(j & (unsigned long long)(A.q_cap - 1));
+            const int epoch = (int)(j >> A.q_cap_log2) + 1;
+            // at most K records are in flight and the ring is larger, so the slot's previous record (item j - cap) was
+            // claimed long ago; wait for its reader all the same
+            volatile int* seq = &r->seq;
+            const int free_mark = epoch == 1 ? 0 : 1 - epoch;
+            if (*seq != free_mark) wait_for_slot(seq, free_mark);
+            r->traj = traj; r->k = k; r->G = G; r->S = S; r->L2 = L2;
 #pragma unroll
-              for (int i = 0; i < D; ++i) r->x[i] = x[i];
-            }
+            for (int i = 0; i < D; ++i) r->x[i] = x[i];
+            __threadfence();
+            *seq = epoch;
+            alive = false;
           }
-          break;
         }
       }
-      const unsigned need = __ballot_sync(FULL, !alive && !exhausted);
+      // (c) idle lanes claim the next item: a fresh trajectory, or the index of a continuation record to wait for
+      const unsigned need = __ballot_sync(FULL, !alive && !exhausted && !pending);
       if (need) {
         unsigned long long base = 0;
         const int leader = __ffs(need) - 1;
         if (lane == leader) base = atomicAdd(A.counter, (unsigned long long)__popc(need));
         base = __shfl_sync(FULL, base, leader);
-        if (!alive && !exhausted) {
+        if (!alive && !exhausted && !pending) {
           const long long idx = (long long)base + __popc(need & ((1u << lane) - 1u));
-          if (idx < n_cont) {
-            const Rec* r = reinterpret_cast<const Rec*>(A.cont_in) + idx;
-            traj = r->traj; k = r->k; G = r->G; S = r->S; L2 = r->L2; alive = true;
-#pragma unroll
-            for (int i = 0; i < D; ++i) x[i] = r->x[i];
-            const int rem = k % A.ckpt_every;
-            ck = rem ? A.ckpt_every - rem : 0;
-          } else if (idx < n_work) {
-            traj = idx - n_cont; k = 0; ck = 0; alive = true;
+          if (idx < A.K) {
+            traj = idx; k = 0; ck = 0; alive = true;
             G = 0; S = 0; L2 = 0;
 #pragma unroll
             for (int i = 0; i < D; ++i) x[i] = F64 ? (real)A.x0_d[i] : (real)A.x0_f[i];
+          } else if (sliced) {
+            pending = true; traj = idx - A.K;
           } else {
             exhausted = true;
           }
         }
       }
-      if (!__any_sync(FULL, alive)) break;
+      // (d) lanes waiting for a record look at their slot; the other lanes of the warp are not held up
+      if (sliced && pending) {
+        Rec* r = ring + (traj & (A.q_cap - 1));
+        const int epoch = (int)(traj >> A.q_cap_log2) + 1;
+        volatile int* seq = &r->seq;
+        if (*seq == epoch) {
+          __threadfence();
+          const volatile Rec* v = r;
+          traj = v->traj; k = v->k; G = v->G; S = v->S; L2 = v->L2;
+#pragma unroll
+          for (int i = 0; i < D; ++i) x[i] = v->x[i];
+          *seq = -epoch;
+          alive = true; pending = false;
+          const int rem = k % A.ckpt_every;
+          ck = rem ? A.ckpt_every - rem : 0;
+        } else if (*reinterpret_cast<volatile unsigned long long*>(A.q_ctrl + 2) >= (unsigned long long)A.K) {
+          pending = false; exhausted = true;      // every trajectory has completed: no record will ever arrive
+        }
+      }
+      if (!__any_sync(FULL, alive)) {
+        if (!__any_sync(FULL, pending)) break;
+        park_idle_warp(&(ring + (traj & (A.q_cap - 1)))->seq, (int)(traj >> A.q_cap_log2) + 1, pending, A.q_ctrl + 2,
+                       (unsigned long long)A.K);
+        it |= (unsigned)(SPB - 1);                  // stay on a boundary: the refill block above takes it from here
+        continue;
+      }
       if (!inject) {
         const unsigned long long gt = (unsigned long long)(A.traj_offset + traj);
 #pragma unroll
@@ -336,7 +393,7 @@ __global__ void __launch_bounds__(128) rollout_fwd_kernel(const __grid_constant_
           if (A.logw) ((float*)A.logw)[traj] = (float)G - (float)S_prev;
         }
         A.T[traj] = k;
-        alive = false;
+        alive = false; fin = true;
       } else {
         G = add_rn(G, r);
 #pragma unroll
@@ -356,7 +413,7 @@ __global__ void __launch_bounds__(128) rollout_fwd_kernel(const __grid_constant_
             if (A.logw) ((float*)A.logw)[traj] = (float)G - (float)S;
           }
           A.T[traj] = -1;
-          alive = false;
+          alive = false; fin = true;
         }
       }
     }

@@ -29,53 +29,39 @@ static int launch_fwd_variant(const float* params_host, const FwdArgs& args, int
     if (grid > need) grid = need;
   }
   if (grid < 1) grid = 1;
-  // ---- single launch: small batches, or no scratch for continuation records
-  const long long lanes = grid * block;
-  const bool compact = block == 128 && args.ws_cont_buf[0] != nullptr && lanes <= args.ws_cont_capacity &&
-                       getenv("RLSDE_FWD_NO_COMPACTION") == nullptr;
+  // Time slicing (rollout_fwd.cuh): large batches only, and only if the caller's workspace holds a ring with one record
+  // per trajectory plus one per lane.  RLSDE_FWD_QUANTUM: passes per slice (tuning knob; 0 = run to completion).
   FwdArgs a = args;
-  a.K_fresh = args.K;
-  a.cont_in = nullptr; a.cont_count_in = nullptr; a.cont_out = nullptr; a.cont_count_out = nullptr;
-  a.round_steps = 0xffffffffu; a.drain_steps = 0xffffffffu;
-  a.counter = args.ws_work_counters;
-  if (!compact) {
-    kern<<<(unsigned)grid, block, 0, stream>>>(W, a);
-    note_kernel_launches(1);
-    return (int)cudaGetLastError();
+  // Passes per slice.  The launch's tail is ~4 slices of the slowest warp; a hand-off every 8 passes costs ~3 % in steady
+  // state.  Measured at n_steps_lim = 1000, 1e6 trajectories, 24 % of them running into the limit: 24.3 / 24.5 / 24.9 /
+  // 25.4 / 27.8 ms at 4 / 8 / 16 / 32 / 128 passes, 27.8 ms without slicing -> 1/128 of the pass budget, between 8 and 128.
+  // Training rollouts (RLSDE_F_STORE_PATH) run to completion: their launches end with a handful of very long
+  // trajectories whose sequential length no schedule can hide (K = 4e5, limit 4000: 22.6 ms unsliced, 23.2-24.2 ms sliced).
+  const long long lim_eff = (args.flags & RLSDE_F_NOISE_INJECTED) && args.noise_steps < args.n_steps_lim ? args.noise_steps : args.n_steps_lim;
+  int quantum = (int)(lim_eff / 128 > 128 ? 128 : (lim_eff / 128 < 8 ? 8 : lim_eff / 128));
+  if (args.flags & RLSDE_F_STORE_PATH) quantum = 0;
+  if (const char* e = getenv("RLSDE_FWD_QUANTUM")) quantum = atoi(e);
+  if (quantum > 0) {                                      // a power of two, at least one noise block (4 passes)
+    int q2 = 4;
+    while (q2 < quantum && q2 < (1 << 30)) q2 <<= 1;
+    quantum = q2;
   }
-  // ---- tail compaction.  The main launch stops DRAIN iterations after the work counter runs dry: its live
-  // lanes dump their trajectories (24 B each at d = 1) and leave.  Resume rounds then re-pack the survivors
-  // into dense warps, each round running a bounded number of passes; as trajectories finish, fewer warps stay
-  // resident and the remaining ones run faster.  Without this, warps stay resident until the last of their 32
-  // lanes has finished and ~15 % of the executed passes of the 1e6-trajectory workload are idle lanes.
-  a.cont_out = args.ws_cont_buf[0];
-  a.cont_count_out = args.ws_cont_counts + 0;
-  a.drain_steps = 32;
+  const long long lanes = grid * block;
+  long long need_cap = 1;
+  int cap_log2 = 0;
+  while (need_cap < args.K + lanes) { need_cap <<= 1; ++cap_log2; }      // power of two: slot = index & (cap - 1)
+  const size_t rec = sizeof(ContRec<D, F64>);
+  if (block == 128 && quantum > 0 && args.q_ring != nullptr && (size_t)need_cap * rec <= (size_t)args.q_cap) {
+    a.q_cap = need_cap;                                  // args.q_cap came in as the BYTES available for the ring
+    a.q_cap_log2 = cap_log2;
+    a.q_quantum = quantum;
+    cudaError_t e = cudaMemsetAsync(a.q_ring, 0, (size_t)need_cap * rec, stream);
+    if (e != cudaSuccess) return (int)e;
+  } else {
+    a.q_ring = nullptr; a.q_cap = 0; a.q_cap_log2 = 0; a.q_quantum = 0;
+  }
   kern<<<(unsigned)grid, block, 0, stream>>>(W, a);
-  const long long lim = (args.flags & RLSDE_F_NOISE_INJECTED) && args.noise_steps < args.n_steps_lim ? args.noise_steps : args.n_steps_lim;
-  long long done = 0;
-  unsigned budget = 96;
-  int r = 0;
-  for (; r < 24 && done < lim; ++r) {
-    FwdArgs b = a;
-    b.K_fresh = 0;
-    b.counter = args.ws_work_counters + 1 + r;
-    b.cont_in = args.ws_cont_buf[r & 1]; b.cont_count_in = args.ws_cont_counts + r;
-    b.cont_out = args.ws_cont_buf[(r + 1) & 1]; b.cont_count_out = args.ws_cont_counts + r + 1;
-    b.round_steps = budget; b.drain_steps = 0xffffffffu;
-    kern<<<(unsigned)grid, block, 0, stream>>>(W, b);
-    done += budget;
-    if (r & 1) budget = budget < (1u << 20) ? budget + budget / 2 : budget;   // 96 96 144 144 216 216 324 ...
-    budget = (budget + 3u) & ~3u;
-  }
-  FwdArgs f = a;                       // whatever is left runs to completion
-  f.K_fresh = 0;
-  f.counter = args.ws_work_counters + 1 + r;
-  f.cont_in = args.ws_cont_buf[r & 1]; f.cont_count_in = args.ws_cont_counts + r;
-  f.cont_out = nullptr; f.cont_count_out = nullptr;
-  f.round_steps = 0xffffffffu; f.drain_steps = 0xffffffffu;
-  kern<<<(unsigned)grid, block, 0, stream>>>(W, f);
-  note_kernel_launches(r + 2);          // main launch + r resume rounds + the run-to-completion launch
+  note_kernel_launches(1);
   return (int)cudaGetLastError();
 }
 

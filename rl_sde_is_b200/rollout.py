@@ -55,12 +55,13 @@ def flat_parameters(model):
 _workspaces = {}
 
 
-def _workspace(device):
-    # one scratch buffer per (device, stream): the work counters inside must not be shared by concurrent launches
+def _workspace(device, K=0):
+    """Scratch buffer for the library, one per (device, stream): the work counters inside must not be shared by concurrent
+    launches.  Sized by the largest batch seen (the forward rollout keeps one 24..168-byte record per trajectory there)."""
     key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+    n = int(L.load().rlsde_workspace_bytes(int(K)))
     ws = _workspaces.get(key)
-    if ws is None:
-        n = L.load().rlsde_workspace_bytes(0)
+    if ws is None or ws.numel() < n:
         ws = torch.empty(n, dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
@@ -158,7 +159,7 @@ def rollout_forward(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=10**6, 
     l2 = torch.empty(K, dtype=real, device=dev) if pol is not None else None
     logw = torch.empty(K, dtype=real, device=dev) if want_logw else None
     stats = torch.zeros(L.RLSDE_NSTATS, dtype=torch.float64, device=dev)
-    ws = _workspace(dev)
+    ws = _workspace(dev, K)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = lib.rlsde_rollout_fwd(env_c, mlp_c, params_host.ctypes.data, cfg, _ptr(noise), _ptr(pol), _ptr(G), _ptr(S),
@@ -216,7 +217,7 @@ def rollout_transitions(env_c, mlp_c, params_host, K, *, seed=0, n_max=10**6, no
     S = torch.empty(K, dtype=real, device=dev)
     T2 = torch.empty(K, dtype=torch.int32, device=dev)
     stats = torch.zeros(L.RLSDE_NSTATS, dtype=torch.float64, device=dev)
-    ws = _workspace(dev)
+    ws = _workspace(dev, K)
     if n > 0:
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
@@ -301,7 +302,7 @@ def rollout_loss_and_grad(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=1
     cfg.ckpt_stride = (lim_eff + cfg.ckpt_every - 1) // cfg.ckpt_every
     cfg.flags = flags
     path = torch.empty((K, cfg.ckpt_stride, env_c.d), dtype=torch.float32, device=dev)
-    ws = _workspace(dev)
+    ws = _workspace(dev, K)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = lib.rlsde_rollout_fwd(env_c, mlp_c, params_host.ctypes.data, cfg, _ptr(noise), 0, _ptr(G), _ptr(S), _ptr(T), 0, 0,

@@ -570,3 +570,59 @@ def test_fused_training_step_equals_autograd_route(golden, fixture, prefix):
     assert float(la.detach()) == lb and np.array_equal(ra, rb) and np.array_equal(sa, sb)
     for (k, p1), (_, p2) in zip(ma.named_parameters(), mb.named_parameters()):
         assert torch.equal(p1.grad, p2.grad), k
+
+
+# ------------------------------------------------------------------------------ time-sliced scheduling of K1
+@pytest.mark.parametrize("f64", [False, True])
+def test_time_sliced_rollout_is_bit_identical(monkeypatch, f64):
+    """The forward kernel's FIFO of continuation records (slices of RLSDE_FWD_QUANTUM passes) changes only the schedule:
+    every per-trajectory output equals the run-to-completion launch bit for bit, whatever the quantum; so do the state
+    checkpoints (hence the gradient) and the transition stream."""
+    from rl_sde_is_b200 import _lib as L, rollout as R
+    from rl_sde_is_b200.models import DeterministicPolicy
+    env = _make_env(1, 1.0, 1.0, 0.005)
+    torch.manual_seed(11)
+    model = DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    model.policy[4].bias.data.fill_(0.4)
+    params = R.flat_parameters(model).detach().numpy()
+    rule = L.HIT_X0_IN_LB_RB if f64 else L.HIT_ALL_GE_LB
+    env_c, mlp_c = R.env_struct(env, rule), L.make_mlp(1, 32)
+    K, lim = 60000, 700                     # > 148 x 128 lanes' worth: the persistent-grid path; ~15 % never hit within lim
+    outs = {}
+    for q in ("0", "4", "32", "128"):
+        monkeypatch.setenv("RLSDE_FWD_QUANTUM", q)
+        o = R.rollout_forward(env_c, mlp_c, params, K, seed=123, n_steps_lim=lim, state_f64=f64, stoch_int="exact", want_logw=True,
+                              store_path=not f64, ckpt_every=4)
+        outs[q] = (o.G.clone(), o.S.clone(), o.T.clone(), o.logw.clone(), None if f64 else o.path.clone(), o.stats.copy())
+        if not f64 and q in ("0", "32"):
+            outs[q] += (R.rollout_backward(env_c, mlp_c, params, o, 1.0 / K).clone(),)
+    ref_out = outs["0"]
+    assert int((ref_out[2] < 0).sum()) > 0.05 * K and int((ref_out[2] >= 0).sum()) > 0.5 * K
+    for q in ("4", "32", "128"):
+        for a, b in zip(ref_out[:4], outs[q][:4]):
+            assert torch.equal(a, b), q
+        assert np.array_equal(ref_out[5], outs[q][5]), q
+        if not f64:
+            # checkpoints: compare what the reverse pass reads (slots up to the hit index)
+            T = ref_out[2].cpu().numpy()
+            n_ck = np.where(T >= 0, T // 4 + 1, (lim + 3) // 4)
+            mask = torch.as_tensor(np.arange(ref_out[4].shape[1])[None, :] < n_ck[:, None], device=ref_out[4].device)
+            assert torch.equal(ref_out[4][..., 0][mask], outs[q][4][..., 0][mask]), q
+    if not f64:
+        assert torch.equal(outs["0"][6], outs["32"][6])
+
+
+def test_time_sliced_transition_stream(monkeypatch):
+    from rl_sde_is_b200.approximate_methods import sample_transitions
+    from rl_sde_is_b200.models import DeterministicPolicy
+    env = _make_env(1, 1.0, 1.0, 0.005)
+    torch.manual_seed(3)
+    model = DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    model.policy[4].bias.data.fill_(1.0)
+    res = {}
+    for q in ("0", "16"):
+        monkeypatch.setenv("RLSDE_FWD_QUANTUM", q)
+        tr = sample_transitions(env, model, 30000, 3000, seed=5, order="trajectory")
+        res[q] = tr
+    for name in ("states", "actions", "rewards", "next_states", "done", "counts"):
+        assert torch.equal(getattr(res["0"], name), getattr(res["16"], name)), name
