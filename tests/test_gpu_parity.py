@@ -626,3 +626,64 @@ def test_time_sliced_transition_stream(monkeypatch):
         res[q] = tr
     for name in ("states", "actions", "rewards", "next_states", "done", "counts"):
         assert torch.equal(getattr(res["0"], name), getattr(res["16"], name)), name
+
+
+# ------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("K", [0, 1, 31, 33, 148 * 128, 148 * 128 + 1])
+def test_rollout_ragged_batch_sizes(K):
+    """Empty, single, ragged-warp batches and both sides of the small-batch / persistent-grid switch: every trajectory's
+    result is a function of (seed, trajectory id) only, so a batch is a prefix of a larger one, bit for bit."""
+    from rl_sde_is_b200 import _lib as L, rollout as R
+    from rl_sde_is_b200.models import DeterministicPolicy
+    env = _make_env(1, 1.0, 1.0, 0.005)
+    torch.manual_seed(2)
+    model = DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    model.policy[4].bias.data.fill_(1.2)
+    params = R.flat_parameters(model).detach().numpy()
+    env_c, mlp_c = R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(1, 32)
+    big = R.rollout_forward(env_c, mlp_c, params, 148 * 128 + 64, seed=4, n_steps_lim=3000, kernel="thread")
+    out = R.rollout_forward(env_c, mlp_c, params, K, seed=4, n_steps_lim=3000, kernel="thread")
+    assert out.G.shape == (K,) and out.T.shape == (K,)
+    assert torch.equal(out.G, big.G[:K]) and torch.equal(out.S, big.S[:K]) and torch.equal(out.T, big.T[:K])
+    st = out.stats
+    assert st[L.ST_N] == K and st[L.ST_N_UNFINISHED] == int((out.T < 0).sum())
+    if K:
+        assert st[L.ST_USEFUL_STEPS] == float(torch.where(out.T >= 0, out.T + 1, torch.full_like(out.T, 3000)).sum())
+
+
+def test_rollout_pass_budget_of_one_and_short_noise():
+    """n_steps_lim = 1: nothing can be detected (the hit test runs on the current state, x0 is outside the target set);
+    injected noise shorter than the budget caps the rollout at the noise length."""
+    from rl_sde_is_b200 import _lib as L, rollout as R
+    from rl_sde_is_b200.models import DeterministicPolicy
+    env = _make_env(1, 1.0, 1.0, 0.005)
+    torch.manual_seed(2)
+    model = DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    params = R.flat_parameters(model).detach().numpy()
+    env_c, mlp_c = R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(1, 32)
+    out = R.rollout_forward(env_c, mlp_c, params, 500, seed=1, n_steps_lim=1)
+    assert bool((out.T == -1).all()) and out.stats[L.ST_USEFUL_STEPS] == 500
+    u0 = float(model(torch.tensor([[-1.0]])).item())
+    np.testing.assert_allclose(out.G.cpu().numpy(), -(1 + 0.5 * u0 * u0) * 0.005, rtol=1e-5)
+    noise = R.noise_fill(3, 500, 1, 7, env.dt)
+    capped = R.rollout_forward(env_c, mlp_c, params, 500, n_steps_lim=10**6, noise=noise)
+    assert bool((capped.T == -1).all()) and capped.stats[L.ST_USEFUL_STEPS] == 500 * 7
+
+
+@pytest.mark.parametrize("Ns,Na", [(6, 4), (7, 5), (16, 33), (2, 2)])
+def test_dp_sweep_even_and_odd_column_counts(Ns, Na):
+    """The sweep reads 16-byte pairs; with an even column count all rows share one alignment (one partial array), with
+    an odd count they alternate (two).  Random tensors of both kinds against the NumPy contraction."""
+    from types import SimpleNamespace
+    from rl_sde_is_b200.tabular_dp_sweeps import DeviceTables
+    rng = np.random.default_rng(Ns * 100 + Na)
+    P = rng.random((Ns, Ns, Na))
+    R_ = -rng.random((Ns, Na))
+    in_ts = rng.random(Ns) < 0.3
+    v = rng.standard_normal(Ns)
+    T = DeviceTables(SimpleNamespace(is_in_ts=in_ts), R_, P)
+    got = T.sweep(v, 0.9).cpu().numpy()
+    want = R_ + (1 - in_ts[:, None].astype(float)) * 0.9 * np.einsum("psa,p->sa", P, v)
+    np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-14)
+    vmax, arg = T.rowmax(torch.as_tensor(want, device="cuda"), want_arg=True)
+    assert np.array_equal(arg.cpu().numpy(), want.argmax(axis=1)) and np.array_equal(vmax.cpu().numpy(), want.max(axis=1))
