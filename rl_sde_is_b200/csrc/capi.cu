@@ -88,6 +88,9 @@ static int fill_cfg(const rlsde_rollout_cfg* cfg, FwdArgs& A) {
   A.K_global = cfg->K_global > 0 ? cfg->K_global : cfg->K;
   A.seed = cfg->seed; A.n_steps_lim = cfg->n_steps_lim; A.noise_steps = cfg->noise_steps;
   A.flags = cfg->flags; A.ckpt_every = cfg->ckpt_every > 0 ? cfg->ckpt_every : 1; A.ckpt_stride = cfg->ckpt_stride;
+  A.ckpt_log2 = -1;
+  for (int b = 0; b < 31; ++b)
+    if (A.ckpt_every == (1 << b)) A.ckpt_log2 = b;
   A.n_grid = cfg->n_grid; A.grid_lo = cfg->grid_lo; A.grid_hi = cfg->grid_hi; A.grid_h = cfg->grid_h;
   return RLSDE_OK;
 }
@@ -212,7 +215,9 @@ static int rollout_fwd_impl(const rlsde_env* env, const rlsde_mlp* mlp, const fl
   if (lrc != 0) return cuda_fail((cudaError_t)lrc, "rollout_fwd launch");
   if (stats_dev) {
     double* partial = (double*)((char*)workspace_dev + WS_COUNTER_BYTES);
-    lrc = launch_reduce_stats(A.K, A.n_steps_lim, (A.flags & RLSDE_F_STATE_F64) != 0, G_dev, S_dev, T_dev, l2_dev, logw_dev,
+    // passes an undetected trajectory has executed: the budget, or the injected noise if that is shorter
+    const long long lim_eff = (A.flags & RLSDE_F_NOISE_INJECTED) && A.noise_steps < A.n_steps_lim ? A.noise_steps : A.n_steps_lim;
+    lrc = launch_reduce_stats(A.K, lim_eff, (A.flags & RLSDE_F_STATE_F64) != 0, G_dev, S_dev, T_dev, l2_dev, logw_dev,
                               stats_dev, partial, stream);
     if (lrc != 0) return cuda_fail((cudaError_t)lrc, "reduce_stats launch");
   }

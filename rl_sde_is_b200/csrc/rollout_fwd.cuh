@@ -56,6 +56,7 @@ struct FwdArgs {
   long long n_steps_lim, noise_steps;
   unsigned flags;
   int ckpt_every;
+  int ckpt_log2;                 // log2(ckpt_every) if it is a power of two (checkpoint index = k >> ckpt_log2), else -1
   long long ckpt_stride;
   long long n_grid;
   double grid_lo, grid_hi, grid_h;
@@ -321,7 +322,8 @@ __global__ void __launch_bounds__(128, (D == 1 ? 8 : 1)) rollout_fwd_kernel(cons
     if (alive) {
       if (store_path) {
         if (ck == 0) {
-          float* dst = A.path + ((long long)traj * A.ckpt_stride + k / A.ckpt_every) * D;
+          const int ci = A.ckpt_log2 >= 0 ? (k >> A.ckpt_log2) : (k / A.ckpt_every);      // no integer division per pass
+          float* dst = A.path + ((long long)traj * A.ckpt_stride + ci) * D;
 #pragma unroll
           for (int i = 0; i < D; ++i) dst[i] = (float)x[i];
           ck = A.ckpt_every;

@@ -171,9 +171,10 @@ __global__ void __launch_bounds__(128) rollout_fwd_warp_kernel(const __grid_cons
       }
       if (store_path) {
         if (ck == 0) {
+          const int ci = A.ckpt_log2 >= 0 ? (k >> A.ckpt_log2) : (k / A.ckpt_every);      // no integer division per pass
 #pragma unroll
           for (int i = 0; i < D; ++i)
-            if (lane == i) A.path[((long long)traj * A.ckpt_stride + k / A.ckpt_every) * D + i] = (float)x[i];
+            if (lane == i) A.path[((long long)traj * A.ckpt_stride + ci) * D + i] = (float)x[i];
           ck = A.ckpt_every;
         }
         --ck;

@@ -159,6 +159,8 @@ def rollout_forward(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=10**6, 
     l2 = torch.empty(K, dtype=real, device=dev) if pol is not None else None
     logw = torch.empty(K, dtype=real, device=dev) if want_logw else None
     stats = torch.zeros(L.RLSDE_NSTATS, dtype=torch.float64, device=dev)
+    if K == 0:          # nothing to launch (and empty tensors have no device pointer to hand over)
+        return RolloutOut(G=G, S=S, T=T, l2=l2, logw=logw, path=path, stats_dev=stats, cfg=cfg)
     ws = _workspace(dev, K)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
