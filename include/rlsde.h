@@ -202,6 +202,24 @@ int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
                       const int32_t* T_dev, const float* path_dev, const int64_t* order_dev, double loss_scale,
                       float* grad_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/*
+ * One REINFORCE iteration with everything resident on the device (reinforce_deterministic_core.py:232-243:
+ * zero_grad -> sample_loss_vectorized -> backward -> Adam step), for the latency-bound small-batch regime
+ * (K <= 16 x SMs, hidden width 32; RLSDE_ERR_UNSUPPORTED otherwise): the policy is read from theta_dev (float[P],
+ * state_dict order), the forward rollout, the statistics reduction, the reverse pass and the Adam update are enqueued
+ * back to back and nothing is read back, so consecutive iterations need no host round trip.
+ *   theta_dev, adam_m_dev, adam_v_dev: float[P], updated in place (torch.optim.Adam semantics, amsgrad / weight decay off);
+ *   step_t: 1-based Adam step (bias corrections);  cfg: RLSDE_F_STORE_PATH with ckpt_every == 1, float32 state;
+ *   G/S/T/stats/grad: this iteration's per-trajectory results, statistics record and gradient of
+ *   mean_k(-G_k - sg(G_k) S_k) -- e.g. rows of a device-side log the caller reads once at the end.
+ * A trajectory that does not reach the target set within n_steps_lim contributes nothing to the gradient and is
+ * counted in stats[RLSDE_ST_N_UNFINISHED]; the caller decides what to do about it when it reads the log.
+ */
+int rlsde_reinforce_step(const rlsde_env* env, const rlsde_mlp* mlp, float* theta_dev, float* adam_m_dev, float* adam_v_dev,
+                         const rlsde_rollout_cfg* cfg, const float* noise_dev, double lr, double beta1, double beta2,
+                         double eps, int64_t step_t, float* G_dev, float* S_dev, int32_t* T_dev, float* path_dev,
+                         double* stats_dev, float* grad_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Deterministic fp64 reduction of per-trajectory outputs into a statistics record. */
 int rlsde_reduce_stats(int64_t K, int64_t n_steps_lim, uint32_t flags, const void* G_dev, const void* S_dev,
                        const int32_t* T_dev, const void* l2_dev, const void* logw_dev, double* stats_dev,

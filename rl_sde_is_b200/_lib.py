@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = [
     "rlsde_version", "rlsde_strerror", "rlsde_last_cuda_error", "rlsde_device_info", "rlsde_supported",
     "rlsde_param_count", "rlsde_workspace_bytes", "rlsde_rollout_fwd", "rlsde_rollout_bwd", "rlsde_reduce_stats",
     "rlsde_tables", "rlsde_tables_colsum", "rlsde_env_step", "rlsde_noise_fill",
-    "rlsde_dp_scratch_bytes", "rlsde_dp_sweep", "rlsde_dp_rowmax", "rlsde_rollout_transitions", "rlsde_launch_count",
+    "rlsde_dp_scratch_bytes", "rlsde_dp_sweep", "rlsde_dp_rowmax", "rlsde_rollout_transitions", "rlsde_launch_count", "rlsde_reinforce_step",
 ]
 
 
@@ -96,6 +96,8 @@ def load():
                                       vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.rlsde_rollout_transitions.argtypes = [C.POINTER(RlsdeEnv), C.POINTER(RlsdeMlp), vp, C.POINTER(RlsdeRolloutCfg),
                                               vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.rlsde_reinforce_step.argtypes = [C.POINTER(RlsdeEnv), C.POINTER(RlsdeMlp), vp, vp, vp, C.POINTER(RlsdeRolloutCfg), vp,
+                                         dbl, dbl, dbl, dbl, i64, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.rlsde_rollout_bwd.argtypes = [C.POINTER(RlsdeEnv), C.POINTER(RlsdeMlp), vp, C.POINTER(RlsdeRolloutCfg),
                                       vp, vp, vp, vp, vp, dbl, vp, vp, C.c_size_t, vp]
     lib.rlsde_reduce_stats.argtypes = [i64, i64, u32, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
@@ -109,7 +111,7 @@ def load():
     lib.rlsde_dp_rowmax.argtypes = [vp, i64, i64, vp, vp, vp]
     for name in ("rlsde_device_info", "rlsde_supported", "rlsde_rollout_fwd", "rlsde_rollout_bwd", "rlsde_reduce_stats",
                  "rlsde_tables", "rlsde_tables_colsum", "rlsde_env_step", "rlsde_noise_fill", "rlsde_dp_sweep", "rlsde_dp_rowmax",
-                 "rlsde_rollout_transitions"):
+                 "rlsde_rollout_transitions", "rlsde_reinforce_step"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

@@ -4,6 +4,33 @@
 
 namespace rlsde {
 
+// ------------------------------------------------------------------ Adam (device-resident REINFORCE loop)
+// torch.optim.Adam's update for one flat parameter vector (amsgrad / weight decay / maximize off), the step the
+// reference takes after eff_loss.backward() (reinforce_deterministic_core.py:143-146,243):
+//   m <- m + (g - m)(1 - beta1);  v <- v beta2 + (1 - beta2) g g;  theta <- theta - (lr / bc1) m / (sqrt(v) / sqrt(bc2) + eps)
+__global__ void adam_step_kernel(int P, float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
+                                 float* __restrict__ v, float one_minus_b1, float b2, float one_minus_b2, float eps,
+                                 float step_size, float bc2_sqrt) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float g = grad[p];
+  const float mp = __fmaf_rn(__fsub_rn(g, m[p]), one_minus_b1, m[p]);
+  const float vp = __fadd_rn(__fmul_rn(v[p], b2), __fmul_rn(__fmul_rn(one_minus_b2, g), g));
+  m[p] = mp;
+  v[p] = vp;
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vp), bc2_sqrt), eps);
+  theta[p] = __fsub_rn(theta[p], __fmul_rn(step_size, __fdiv_rn(mp, denom)));
+}
+
+int launch_adam_step(int P, float* theta, const float* grad, float* m, float* v, double lr, double beta1, double beta2,
+                     double eps, long long step_t, cudaStream_t stream) {
+  const double bc1 = 1.0 - pow(beta1, (double)step_t), bc2 = 1.0 - pow(beta2, (double)step_t);
+  adam_step_kernel<<<(P + 127) / 128, 128, 0, stream>>>(P, theta, grad, m, v, (float)(1.0 - beta1), (float)beta2,
+                                                        (float)(1.0 - beta2), (float)eps, (float)(lr / bc1), (float)sqrt(bc2));
+  note_kernel_launches(1);
+  return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ statistics
 // Two-stage fixed-shape reduction: stage 1 = STATS_BLOCKS blocks, each summing a contiguous slice
 // with a fixed in-block tree; stage 2 = one block summing the partials in index order.  The result

@@ -152,7 +152,8 @@ int64_t rlsde_param_count(const rlsde_mlp* mlp) {
   return d * H + H + (int64_t)(mlp->n_hidden - 1) * (H * H + H) + H * o + o;
 }
 
-static size_t ws_fixed_bytes() { return WS_COUNTER_BYTES + WS_STATS_BYTES + bwd_workspace_bytes(); }
+constexpr size_t WS_POLICY_BYTES = 16384;          // device copy of the packed policy (device-resident training step)
+static size_t ws_fixed_bytes() { return WS_COUNTER_BYTES + WS_STATS_BYTES + WS_POLICY_BYTES + bwd_workspace_bytes(); }
 
 size_t rlsde_workspace_bytes(int64_t K) {
   const long long k = K > 0 ? K : 0;
@@ -208,7 +209,7 @@ static int rollout_fwd_impl(const rlsde_env* env, const rlsde_mlp* mlp, const fl
   const bool warp_path = use_warp_kernels(A, mlp->d_hidden, sm, (A.flags & RLSDE_F_STORE_PATH) != 0);
 #define X(D_, H_)                                                                              \
   if (env->d == D_ && mlp->d_hidden == H_)                                                     \
-    lrc = (warp_path && H_ == WARP_H) ? launch_rollout_fwd_warp<D_>(params_host, A, sm, stream) \
+    lrc = (warp_path && H_ == WARP_H) ? launch_rollout_fwd_warp<D_>(params_host, nullptr, A, sm, stream) \
                                       : launch_rollout_fwd<D_, H_>(params_host, A, sm, stream);
   RLSDE_SHAPES(X)
 #undef X
@@ -269,16 +270,66 @@ int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
   if ((rc = device_sm_count(&sm)) != RLSDE_OK) return rc;
   cudaError_t e = cudaMemsetAsync(workspace_dev, 0, WS_COUNTER_BYTES, stream);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
-  float* partial = (float*)((char*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES);
+  float* partial = (float*)((char*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES + WS_POLICY_BYTES);
   int lrc = -1;
   const bool warp_path = use_warp_kernels(A, mlp->d_hidden, sm, true);
 #define X(D_, H_)                                                                                                          \
   if (env->d == D_ && mlp->d_hidden == H_)                                                                                 \
-    lrc = (warp_path && H_ == WARP_H) ? launch_rollout_bwd_warp<D_>(params_host, A, (float)loss_scale, grad_dev, partial, sm, stream) \
+    lrc = (warp_path && H_ == WARP_H) ? launch_rollout_bwd_warp<D_>(params_host, nullptr, A, (float)loss_scale, grad_dev, partial, sm, stream) \
                                       : launch_rollout_bwd<D_, H_>(params_host, A, (float)loss_scale, grad_dev, partial, sm, stream);
   RLSDE_SHAPES(X)
 #undef X
   if (lrc != 0) return cuda_fail((cudaError_t)lrc, "rollout_bwd launch");
+  return RLSDE_OK;
+}
+
+int rlsde_reinforce_step(const rlsde_env* env, const rlsde_mlp* mlp, float* theta_dev, float* adam_m_dev, float* adam_v_dev,
+                         const rlsde_rollout_cfg* cfg, const float* noise_dev, double lr, double beta1, double beta2,
+                         double eps, int64_t step_t, float* G_dev, float* S_dev, int32_t* T_dev, float* path_dev,
+                         double* stats_dev, float* grad_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_env_mlp(env, mlp);
+  if (rc != RLSDE_OK) return rc;
+  if (!theta_dev || !adam_m_dev || !adam_v_dev || !G_dev || !S_dev || !T_dev || !path_dev || !stats_dev || !grad_dev ||
+      !workspace_dev || step_t < 1)
+    return RLSDE_ERR_INVALID_ARG;
+  if (workspace_bytes < ws_fixed_bytes()) return RLSDE_ERR_WORKSPACE;
+  static_assert(sizeof(MlpConst<RLSDE_MAX_D, WARP_H>) <= WS_POLICY_BYTES, "raise WS_POLICY_BYTES");
+  FwdArgs A;
+  memset(&A, 0, sizeof(A));
+  fill_env(env, A);
+  if ((rc = fill_cfg(cfg, A)) != RLSDE_OK) return rc;
+  if ((A.flags & RLSDE_F_STATE_F64) || !(A.flags & RLSDE_F_STORE_PATH) || A.ckpt_every != 1) return RLSDE_ERR_INVALID_ARG;
+  if ((A.flags & RLSDE_F_NOISE_INJECTED) && !noise_dev) return RLSDE_ERR_INVALID_ARG;
+  if (A.K < 1) return RLSDE_ERR_INVALID_ARG;
+  int sm = 0;
+  if ((rc = device_sm_count(&sm)) != RLSDE_OK) return rc;
+  // the device-resident step exists for the latency-bound regime only: warp-per-trajectory kernels
+  if (mlp->d_hidden != WARP_H || A.K > warp_path_max_k(sm) || (A.flags & RLSDE_F_KERNEL_THREAD)) return RLSDE_ERR_UNSUPPORTED;
+  A.noise = noise_dev;
+  A.G = G_dev; A.S = S_dev; A.T = T_dev; A.path = path_dev;
+  A.counter = (unsigned long long*)workspace_dev;
+  A.q_ctrl = (unsigned long long*)workspace_dev;
+  void* W_dev = (char*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES;
+  double* stats_partial = (double*)((char*)workspace_dev + WS_COUNTER_BYTES);
+  float* partial = (float*)((char*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES + WS_POLICY_BYTES);
+  const bool fast = (A.flags & RLSDE_F_TANH_FAST) != 0;
+  const int P = (int)rlsde_param_count(mlp);
+  const long long lim_eff = (A.flags & RLSDE_F_NOISE_INJECTED) && A.noise_steps < A.n_steps_lim ? A.noise_steps : A.n_steps_lim;
+  int lrc = -1;
+#define X(D_, H_)                                                                                                        \
+  if (env->d == D_ && mlp->d_hidden == H_ && H_ == WARP_H) {                                                             \
+    lrc = launch_pack_mlp_const_dev<D_>(theta_dev, W_dev, fast, stream);                                                 \
+    if (lrc == 0) lrc = launch_rollout_fwd_warp<D_>(nullptr, W_dev, A, sm, stream);                                      \
+    if (lrc == 0) lrc = launch_reduce_stats(A.K, lim_eff, false, G_dev, S_dev, T_dev, nullptr, nullptr, stats_dev,       \
+                                            stats_partial, stream);                                                     \
+    if (lrc == 0) lrc = launch_rollout_bwd_warp<D_>(nullptr, W_dev, A, (float)(1.0 / (double)A.K), grad_dev, partial, sm, stream); \
+  }
+  RLSDE_SHAPES(X)
+#undef X
+  if (lrc != 0) return cuda_fail((cudaError_t)lrc, "reinforce_step launch");
+  lrc = launch_adam_step(P, theta_dev, grad_dev, adam_m_dev, adam_v_dev, lr, beta1, beta2, eps, step_t, stream);
+  if (lrc != 0) return cuda_fail((cudaError_t)lrc, "adam_step launch");
   return RLSDE_OK;
 }
 

@@ -54,7 +54,7 @@ struct LaneParams {
   float w2row[WARP_H], b2;    // row `lane` of W2: weights into hidden unit `lane`
   float w3[D];                // column `lane` of W3
   float b3[D];                // head bias (uniform)
-  __device__ __forceinline__ void load(const MlpConst<D, WARP_H>& W, int lane) {
+  __device__ __forceinline__ void load(const MlpConst<D, WARP_H>& W, int lane) {   // W: kernel parameter or device memory
 #pragma unroll
     for (int i = 0; i < D; ++i) { w1[i] = W.W1t[i][lane]; w3[i] = W.W3[i][lane]; b3[i] = W.b3[i]; pin(w1[i]); pin(w3[i]); }
     b1 = W.b1[lane]; pin(b1);
@@ -88,8 +88,11 @@ __device__ __forceinline__ void warp_policy(const LaneParams<D>& P, float* slot,
 
 // ------------------------------------------------------------------------------------------------ forward
 template <int D, bool F64, bool FAST>
-__global__ void __launch_bounds__(128) rollout_fwd_warp_kernel(const __grid_constant__ MlpConst<D, WARP_H> W,
+__global__ void __launch_bounds__(128) rollout_fwd_warp_kernel(const __grid_constant__ MlpConst<D, WARP_H> W_param,
+                                                               const MlpConst<D, WARP_H>* __restrict__ W_dev,
                                                                const __grid_constant__ FwdArgs A) {
+  // the policy comes by value (host parameters) or, for the device-resident training loop, from device memory
+  const MlpConst<D, WARP_H>& W = W_dev != nullptr ? *W_dev : W_param;
   typedef typename RealT<F64>::type real;
   constexpr int SPB = NoisePlan<D>::SPB;
   constexpr int BPP = NoisePlan<D>::BPP;
@@ -233,8 +236,10 @@ __global__ void __launch_bounds__(128) rollout_fwd_warp_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------------ reverse
 // Needs every state (ckpt_every == 1).  Lane j accumulates row j of dW2 / dW1, column j of dW3, entry j of db1 / db2.
 template <int D, bool FAST>
-__global__ void __launch_bounds__(128) rollout_bwd_warp_kernel(const __grid_constant__ MlpConst<D, WARP_H> W,
+__global__ void __launch_bounds__(128) rollout_bwd_warp_kernel(const __grid_constant__ MlpConst<D, WARP_H> W_param,
+                                                               const MlpConst<D, WARP_H>* __restrict__ W_dev,
                                                                const __grid_constant__ FwdArgs A, float* __restrict__ partial) {
+  const MlpConst<D, WARP_H>& W = W_dev != nullptr ? *W_dev : W_param;
   constexpr int H = WARP_H;
   constexpr int P_ = D * H + H + H * H + H + H * D + D;
   __shared__ __align__(16) float slots[4][WARP_H];
@@ -337,10 +342,15 @@ __global__ void __launch_bounds__(128) rollout_bwd_warp_kernel(const __grid_cons
 // largest batch routed to the warp-per-trajectory kernels (above it one trajectory per thread fills the GPU better)
 inline long long warp_path_max_k(int sm_count) { return (long long)sm_count * 16; }
 
+// params_host == nullptr: the policy is read from W_dev (an MlpConst<D, WARP_H> in device memory, see pack_mlp_const_dev)
 template <int D>
-int launch_rollout_fwd_warp(const float* params_host, const FwdArgs& args, int sm_count, cudaStream_t stream);
+int launch_rollout_fwd_warp(const float* params_host, const void* W_dev, const FwdArgs& args, int sm_count, cudaStream_t stream);
 template <int D>
-int launch_rollout_bwd_warp(const float* params_host, const FwdArgs& args, float scale, float* grad, float* partial,
-                            int sm_count, cudaStream_t stream);
+int launch_rollout_bwd_warp(const float* params_host, const void* W_dev, const FwdArgs& args, float scale, float* grad,
+                            float* partial, int sm_count, cudaStream_t stream);
+// theta_dev (flat float32, state_dict order) -> MlpConst<D, WARP_H> in device memory, same rounding as the host packer
+template <int D>
+int launch_pack_mlp_const_dev(const float* theta_dev, void* W_dev, bool fast_tanh, cudaStream_t stream);
+inline size_t mlp_const_bytes_max() { return sizeof(MlpConst<RLSDE_MAX_D, WARP_H>); }
 
 }  // namespace rlsde

@@ -103,6 +103,95 @@ def _loss_and_grads_fused(env, model, K, *, noise=None, seed=None, n_steps_lim=1
     return float(np.float32(stats[L.ST_SUM_LOSS] / K)), G.copy(), (T + 1).astype(np.float64)
 
 
+class _DeviceLoop:
+    """REINFORCE iterations with parameters, Adam state and logs resident on the GPU (``rlsde_reinforce_step``): each
+    iteration is one C call that enqueues rollout, statistics, reverse pass and Adam update; nothing is read back until
+    ``flush()``.  Small batches only (warp-per-trajectory kernels: K <= 16 x SMs, hidden width 32)."""
+
+    def __init__(self, env, model, K, lr, n_iterations, *, n_steps_lim=10**6, tanh="precise", stoch_int="reference", device=None,
+                 betas=(0.9, 0.999), eps=1e-8):
+        self.lib = L.load()
+        self.env, self.model, self.K, self.lr, self.betas, self.eps = env, model, int(K), float(lr), betas, float(eps)
+        d, H = R.policy_shape(model)
+        self.env_c, self.mlp_c = R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(d, H)
+        self.dev = dev = R._cuda_device(device)
+        self.linears = R.policy_linears(model)
+        with torch.no_grad():
+            flat = torch.cat([t.reshape(-1) for lin in self.linears for t in (lin.weight, lin.bias)]).to(torch.float32)
+        self.theta = flat.to(dev)
+        self.m, self.v = torch.zeros_like(self.theta), torch.zeros_like(self.theta)
+        self.grad = torch.empty_like(self.theta)
+        cfg = L.RlsdeRolloutCfg()
+        cfg.K, cfg.traj_offset, cfg.K_global = self.K, 0, self.K
+        cfg.n_steps_lim = int(n_steps_lim)
+        cfg.flags = L.F_STORE_PATH | L.F_KERNEL_WARP | {"precise": 0, "fast": L.F_TANH_FAST}[tanh] \
+            | {"reference": 0, "exact": L.F_STOCH_INT_EXACT}[stoch_int]
+        cfg.ckpt_every, cfg.ckpt_stride = 1, int(n_steps_lim)
+        self.cfg = cfg
+        self.path = torch.empty((self.K, cfg.ckpt_stride, d), dtype=torch.float32, device=dev)
+        self.S = torch.empty(self.K, dtype=torch.float32, device=dev)
+        n = int(n_iterations)
+        self.logG = torch.empty((n, self.K), dtype=torch.float32, device=dev)
+        self.logT = torch.empty((n, self.K), dtype=torch.int32, device=dev)
+        self.logStats = torch.zeros((n, L.RLSDE_NSTATS), dtype=torch.float64, device=dev)
+        self.events = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        self.ws = R._workspace(dev, self.K)
+        self.done, self.read = 0, 0
+        self.events[0].record(torch.cuda.current_stream(dev))
+
+    @staticmethod
+    def supported(env, model, K, rollout_opts, device=None):
+        try:
+            d, H = R.policy_shape(model)
+            if H != 32 or d != env.d or not torch.cuda.is_available():
+                return False
+            if any(k in rollout_opts for k in ("noise", "dist", "ckpt_every", "seed")) or rollout_opts.get("kernel", "auto") == "thread":
+                return False
+            lim = int(rollout_opts.get("n_steps_lim", 10**6))
+            if int(K) * lim * d * 4 > (8 << 30):             # every state is kept for the reverse pass
+                return False
+            n_sm = torch.cuda.get_device_properties(R._cuda_device(device)).multi_processor_count
+            return int(K) <= 16 * n_sm and all(p.device.type == "cpu" for p in model.parameters())
+        except L.RlsdeError:
+            return False
+
+    def step(self):
+        i = self.done
+        self.cfg.seed = _next_seed(None) & 0xFFFFFFFFFFFFFFFF
+        with torch.cuda.device(self.dev):
+            stream = torch.cuda.current_stream(self.dev)
+            rc = self.lib.rlsde_reinforce_step(self.env_c, self.mlp_c, self.theta.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                               self.cfg, 0, self.lr, self.betas[0], self.betas[1], self.eps, i + 1,
+                                               self.logG[i].data_ptr(), self.S.data_ptr(), self.logT[i].data_ptr(),
+                                               self.path.data_ptr(), self.logStats[i].data_ptr(), self.grad.data_ptr(),
+                                               self.ws.data_ptr(), self.ws.numel(), stream.cuda_stream)
+            L.check(rc, "rlsde_reinforce_step")
+            self.events[i + 1].record(stream)
+        self.done = i + 1
+
+    def flush(self):
+        """Synchronise, copy the parameters back into the module and return the log rows of the iterations enqueued since
+        the last flush: ``(first index, losses f32, returns [n, K] f32, time_steps [n, K] f64, seconds per iteration)``."""
+        lo, hi = self.read, self.done
+        torch.cuda.synchronize(self.dev)
+        theta = self.theta.cpu()
+        off = 0
+        with torch.no_grad():
+            for lin in self.linears:
+                for t in (lin.weight, lin.bias):
+                    t.copy_(theta[off:off + t.numel()].view_as(t))
+                    off += t.numel()
+        G = self.logG[lo:hi].cpu().numpy()
+        T = self.logT[lo:hi].cpu().numpy()
+        st = self.logStats[lo:hi].cpu().numpy()
+        if (T < 0).any():
+            raise L.RlsdeError(f"{int((T < 0).sum())} trajectories did not reach the target set within {self.cfg.n_steps_lim} "
+                               "passes; raise n_steps_lim")
+        secs = np.array([self.events[i].elapsed_time(self.events[i + 1]) * 1e-3 for i in range(lo, hi)])
+        self.read = hi
+        return lo, (st[:, L.ST_SUM_LOSS] / self.K).astype(np.float32), G, (T + 1).astype(np.float64), secs
+
+
 class _LossWithAux(torch.autograd.Function):
     """eff_loss = mean_k(-G_k - sg(G_k) S_k) as a differentiable function of the flat policy parameters: forward launches
     the rollout kernel (with state checkpoints), backward the reverse kernel -- what autograd does in the reference over
@@ -137,13 +226,20 @@ class _LossWithAux(torch.autograd.Function):
 
 def reinforce(env, gamma=1., d_hidden_layer=256, n_layers=3, batch_size=1000, lr=1e-3, n_iterations=100, seed=None,
               test_batch_size=1000, test_freq_iterations=100, backup_freq_iterations=None, policy_opt=None,
-              load=False, test=False, live_plot=False, *, save=True, save_fn=None, verbose=True, **rollout_opts):
+              load=False, test=False, live_plot=False, *, save=True, save_fn=None, verbose=True, device_loop=None,
+              **rollout_opts):
     """Training loop with the reference's signature, result dictionary and on-disk layout (:102-336).
 
     ``agent.npz`` and the ``model_n-it{i}`` backups go to the reference's run directory (``utils_path``; pass
     ``save=False`` to keep everything in memory); ``load=True`` returns the stored dictionary, ``load=True, test=True``
     re-tests the stored backups like the reference.  ``save_fn(data, model, iteration)`` is an extra hook called where a
-    backup is written.  Plotting (``live_plot``) is out of the hot path's scope.  ``gamma`` is accepted and unused in
+    backup is written.  Plotting (``live_plot``) is out of the hot path's scope.
+
+    ``device_loop`` (default: whenever the batch is small enough for the warp-per-trajectory kernels): parameters, Adam
+    state and per-iteration logs stay on the GPU and an iteration is one asynchronous C call
+    (``rlsde_reinforce_step``); the host synchronises only where the reference looks at the model (tests, backups, the
+    end).  ``cts`` are then device times per iteration.  ``device_loop=False`` steps ``torch.optim.Adam`` on the CPU
+    module every iteration, like the reference.  ``gamma`` is accepted and unused in
     the loss, as in the reference (:108-117).
     """
     from .approximate_methods import test_policy_vectorized
@@ -206,8 +302,35 @@ def reinforce(env, gamma=1., d_hidden_layer=256, n_layers=3, batch_size=1000, lr
     if test:
         run_test(0)
 
+    if device_loop is None:
+        device_loop = not load and _DeviceLoop.supported(env, model, batch_size, rollout_opts, rollout_opts.get("device"))
+    loop = None
+    if device_loop and not load and n_iterations > 0:
+        loop = _DeviceLoop(env, model, batch_size, lr, n_iterations,
+                           **{k: v for k, v in rollout_opts.items() if k in ("n_steps_lim", "tanh", "stoch_int", "device")})
+
+    def drain():
+        """Bring the device loop's finished iterations into the result arrays (one synchronisation)."""
+        nonlocal returns, time_steps
+        lo, ls, G, T, secs = loop.flush()
+        for j in range(len(ls)):
+            i_ = lo + j
+            returns = np.append(returns, G[j])
+            time_steps = np.append(time_steps, T[j])
+            losses[i_], cts[i_] = ls[j], secs[j]
+            exp_returns[i_], var_returns[i_], exp_time_steps[i_] = np.mean(G[j]), np.var(G[j]), np.mean(T[j])
+            if verbose:
+                print("it.: {:2d}, loss: {:.3e}, exp return: {:.3e}, var return: {:.1e}, ct: {:.3f}".format(
+                    i_, losses[i_], exp_returns[i_], var_returns[i_], cts[i_]))
+
     for i in range(n_iterations):
-        if not load:
+        if loop is not None:
+            loop.step()
+            need_model = (test and (i + 1) % test_freq_iterations == 0) or i + 1 == n_iterations or \
+                (backup_freq_iterations is not None and (i + 1) % backup_freq_iterations == 0)
+            if need_model:
+                drain()
+        elif not load:
             t0 = time.time()
             optimizer.zero_grad()
             if fused_path:     # same kernels as sample_loss_vectorized + backward(), one host synchronisation

@@ -687,3 +687,29 @@ def test_dp_sweep_even_and_odd_column_counts(Ns, Na):
     np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-14)
     vmax, arg = T.rowmax(torch.as_tensor(want, device="cuda"), want_arg=True)
     assert np.array_equal(arg.cpu().numpy(), want.argmax(axis=1)) and np.array_equal(vmax.cpu().numpy(), want.max(axis=1))
+
+
+# ------------------------------------------------------------------------------ device-resident REINFORCE loop
+def test_device_resident_training_loop_matches_host_loop():
+    """reinforce(device_loop=True) -- parameters, Adam state and logs on the GPU, one asynchronous C call per iteration --
+    follows reinforce(device_loop=False) (torch.optim.Adam on the CPU module after every fused step): same Philox keys,
+    same kernels, so losses / returns / hit passes of iteration 0 are identical and the trajectories of the parameters
+    stay together to float32 rounding of the Adam update."""
+    from rl_sde_is_b200.environments import DoubleWellStoppingTime1D
+    from rl_sde_is_b200.reinforce_deterministic_core import reinforce
+    env = DoubleWellStoppingTime1D(beta=1.0, alpha=1.0, dt=0.005)
+    kw = dict(d_hidden_layer=32, batch_size=64, lr=1e-2, n_iterations=6, seed=3, verbose=False, save=False)
+    host = reinforce(env, device_loop=False, **kw)
+    dev = reinforce(env, device_loop=True, **kw)
+    assert np.array_equal(host["returns"][:64], dev["returns"][:64]) and np.array_equal(host["time_steps"][:64], dev["time_steps"][:64])
+    assert host["losses"][0] == dev["losses"][0]
+    np.testing.assert_allclose(dev["losses"], host["losses"], rtol=2e-3)
+    np.testing.assert_allclose(dev["exp_time_steps"], host["exp_time_steps"], rtol=2e-2)
+    for (k, a), (_, b) in zip(host["model"].named_parameters(), dev["model"].named_parameters()):
+        np.testing.assert_allclose(b.detach().numpy(), a.detach().numpy(), rtol=0, atol=2e-4, err_msg=k)
+    assert dev["cts"].shape == (6,) and np.all(dev["cts"] > 0) and dev["returns"].shape == (6 * 64,)
+    # one Adam step on the device equals torch.optim.Adam's to float32 rounding
+    m0 = reinforce(env, device_loop=False, **{**kw, "n_iterations": 1})["model"]
+    m1 = reinforce(env, device_loop=True, **{**kw, "n_iterations": 1})["model"]
+    for (k, a), (_, b) in zip(m0.named_parameters(), m1.named_parameters()):
+        np.testing.assert_allclose(b.detach().numpy(), a.detach().numpy(), rtol=0, atol=3e-7, err_msg=k)
