@@ -51,27 +51,27 @@ inline size_t bwd_workspace_bytes() { return (size_t)BWD_MAX_WARPS * BWD_MAX_PAR
         "f"((w)[2 * (o) + 0]), "f"((w)[2 * (o) + 1]), "f"((w)[2 * (o) + 2]), "f"((w)[2 * (o) + 3]),    \
         "f"((w)[2 * (o) + 4]), "f"((w)[2 * (o) + 5]), "f"((w)[2 * (o) + 6]), "f"((w)[2 * (o) + 7]))
 
-// XOR swizzle of a [32 lanes][H] float tile at float4 granularity: a lane writing its own row with
-// STS.128, a broadcast read of one row, and a read of one column element per lane are all conflict-free.
-#ifndef RLSDE_BWD_PAD
-#define RLSDE_BWD_PAD 0      // 1: rows padded to H + 4 floats instead of the XOR swizzle (fewer instructions, measured slower)
-#endif
-template <int H>
+// Layout of a [32 lanes][H] float tile in shared memory.  Both variants make a lane writing its own row with STS.128, a
+// broadcast read of one row and a read of one column element per lane conflict-free:
+//   PAD = false: XOR swizzle at float4 granularity (no extra memory, ~1 450 integer instructions per pass for addresses);
+//   PAD = true:  rows padded to H + 4 floats (plain addresses).
+// Measured (tools/bench_train.py): at d = 1, where the kernel runs 4 blocks per SM, the padded layout is 19 % faster
+// (57.7 -> 46.8 ms: with four warps per scheduler the instruction count is what limits); at 2 blocks per SM (d >= 2) the
+// swizzle is 3-5 % faster (the address arithmetic fills issue slots that would idle anyway).
+constexpr bool bwd_tiles_padded(int D) { return D == 1; }
+template <int H, bool PAD>
 __device__ __forceinline__ int swz(int row, int col) {
-#if RLSDE_BWD_PAD
-  return row * (H + 4) + col;
-#else
-  return row * H + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3));
-#endif
+  if constexpr (PAD) return row * (H + 4) + col;
+  else return row * H + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3));
 }
-template <int H>
-__host__ __device__ constexpr int tile_floats() { return 32 * (H + (RLSDE_BWD_PAD ? 4 : 0)); }
+template <int H, bool PAD>
+__host__ __device__ constexpr int tile_floats() { return 32 * (H + (PAD ? 4 : 0)); }
 
-template <int H>
+template <int H, bool PAD>
 __device__ __forceinline__ void stage_row(float* tile, int lane, const float (&v)[H]) {
 #pragma unroll
   for (int q = 0; q < H / 4; ++q)
-    *reinterpret_cast<float4*>(tile + swz<H>(lane, 4 * q)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    *reinterpret_cast<float4*>(tile + swz<H, PAD>(lane, 4 * q)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
 // cached Philox block per lane for out-of-order (reverse) access to the increments
@@ -137,15 +137,16 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MIN_BLOCKS(D)) rollout_bwd_kern
                                                           const __grid_constant__ FwdArgs A, float* __restrict__ partial) {
   static_assert(H == 32 || H == 64, "column-per-lane accumulation needs H in {32, 64}");
   constexpr int CPL = H / 32;                 // columns of the HxH block owned by a lane
+  constexpr bool PAD = bwd_tiles_padded(D);
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int P = D * H + H + H * H + H + H * D + D;
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
-  float* tileH1 = smem + (size_t)warp_in_block * (2 * tile_floats<H>() + 64 * D);  // first-layer activations [32][H]
-  float* tileB = tileH1 + tile_floats<H>();                                        // h2, then dz2, then dz1  [32][H]
-  float* vecA = tileB + tile_floats<H>();                                          // a or x                  [32][D]
+  float* tileH1 = smem + (size_t)warp_in_block * (2 * tile_floats<H, PAD>() + 64 * D);  // first-layer activations [32][H]
+  float* tileB = tileH1 + tile_floats<H, PAD>();                                        // h2, then dz2, then dz1  [32][H]
+  float* vecA = tileB + tile_floats<H, PAD>();                                          // a or x                  [32][D]
   const bool inject = (A.flags & RLSDE_F_NOISE_INJECTED) != 0;
   const bool s_exact = (A.flags & RLSDE_F_STOCH_INT_EXACT) != 0;
   const int C = A.ckpt_every;
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MIN_BLOCKS(D)) rollout_bwd_kern
         {
           float h1[H];
           mlp_forward_keep<D, H, FAST>(W, x, h1, h2, u);
-          if (!phase_a) stage_row<H>(tileH1, lane, h1);   // h1 leaves the registers here; re-read when needed
+          if (!phase_a) stage_row<H, PAD>(tileH1, lane, h1);   // h1 leaves the registers here; re-read when needed
         }
         nc.get(A, inject, ok, traj, j, dB);
         if (phase_a) {
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MIN_BLOCKS(D)) rollout_bwd_kern
           a[i] = v;
         }
         // head: dW3[k][col] += a_k h2[col], db3[k] += a_k;  dh2 = W3^T a;  dz2 = dh2 (1 - h2^2)
-        stage_row<H>(tileB, lane, h2);
+        stage_row<H, PAD>(tileB, lane, h2);
 #pragma unroll
         for (int i = 0; i < D; ++i) vecA[lane * D + i] = a[i];
         __syncwarp();
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MIN_BLOCKS(D)) rollout_bwd_kern
             for (int i = 0; i < D; ++i) ar[i] = vecA[r * D + i];
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
-              const float hv = tileB[swz<H>(r, lane + 32 * c)];
+              const float hv = tileB[swz<H, PAD>(r, lane + 32 * c)];
 #pragma unroll
               for (int i = 0; i < D; ++i) pW3[c][i] = fmaf(ar[i], hv, pW3[c][i]);
             }
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MIN_BLOCKS(D)) rollout_bwd_kern
       // hidden-hidden block: dW2[:, col] += dz2 h1[col], db2[col] += dz2[col]
 #pragma unroll
       for (int q = 0; q < H / 4; ++q)
-        *reinterpret_cast<ulonglong2*>(tileB + swz<H>(lane, 4 * q)) = make_ulonglong2(dz2[2 * q], dz2[2 * q + 1]);
+        *reinterpret_cast<ulonglong2*>(tileB + swz<H, PAD>(lane, 4 * q)) = make_ulonglong2(dz2[2 * q], dz2[2 * q + 1]);
       __syncwarp();
       float pb2[CPL];
 #pragma unroll
@@ -299,13 +300,13 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MIN_BLOCKS(D)) rollout_bwd_kern
         float hv[CPL];
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
-          hv[c] = tileH1[swz<H>(r, lane + 32 * c)];
-          pb2[c] += tileB[swz<H>(r, lane + 32 * c)];
+          hv[c] = tileH1[swz<H, PAD>(r, lane + 32 * c)];
+          pb2[c] += tileB[swz<H, PAD>(r, lane + 32 * c)];
         }
 #pragma unroll
         for (int q = 0; q < H / 4; q += 2) {
-          const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(tileB + swz<H>(r, 4 * q));
-          const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(tileB + swz<H>(r, 4 * q + 4));
+          const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(tileB + swz<H, PAD>(r, 4 * q));
+          const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(tileB + swz<H, PAD>(r, 4 * q + 4));
 #pragma unroll
           for (int c = 0; c < CPL; ++c) RLSDE_FMA2X4_REG(gW2[c], 2 * q, hv[c], w0.x, w0.y, w1.x, w1.y);
         }
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MIN_BLOCKS(D)) rollout_bwd_kern
       for (int i = 0; i < D; ++i) dxa[i] = 0.f;
 #pragma unroll
       for (int q = 0; q < H / 4; ++q) {
-        const float4 hq = *reinterpret_cast<const float4*>(tileH1 + swz<H>(lane, 4 * q));
+        const float4 hq = *reinterpret_cast<const float4*>(tileH1 + swz<H, PAD>(lane, 4 * q));
         const float hloc[4] = {hq.x, hq.y, hq.z, hq.w};
         float dq[4], w1q[D][4];
 #pragma unroll
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MIN_BLOCKS(D)) rollout_bwd_kern
 #pragma unroll
           for (int d = 0; d < D; ++d) dxa[d] = fmaf(w1q[d][e], dq[e], dxa[d]);
         }
-        *reinterpret_cast<float4*>(tileB + swz<H>(lane, 4 * q)) = make_float4(dq[0], dq[1], dq[2], dq[3]);
+        *reinterpret_cast<float4*>(tileB + swz<H, PAD>(lane, 4 * q)) = make_float4(dq[0], dq[1], dq[2], dq[3]);
       }
 #pragma unroll
       for (int i = 0; i < D; ++i) vecA[lane * D + i] = x[i];
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MIN_BLOCKS(D)) rollout_bwd_kern
           for (int i = 0; i < D; ++i) xr[i] = vecA[r * D + i];
 #pragma unroll
           for (int c = 0; c < CPL; ++c) {
-            const float dv = tileB[swz<H>(r, lane + 32 * c)];
+            const float dv = tileB[swz<H, PAD>(r, lane + 32 * c)];
             pb1[c] += dv;
 #pragma unroll
             for (int i = 0; i < D; ++i) pW1[c][i] = fmaf(dv, xr[i], pW1[c][i]);

@@ -24,7 +24,7 @@ static int launch_bwd_variant(const float* params_host, const FwdArgs& args, flo
   auto kern = rollout_bwd_kernel<D, H, FAST>;
   int block = 128;
   long long grid;
-  const size_t smem_per_warp = (size_t)(2 * tile_floats<H>() + 64 * D) * sizeof(float);
+  const size_t smem_per_warp = (size_t)(2 * tile_floats<H, bwd_tiles_padded(D)>() + 64 * D) * sizeof(float);
   if (args.K <= (long long)sm_count * 128) {
     block = 32;
     grid = (args.K + 31) / 32;
