@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/rlsde.h"
@@ -207,6 +208,29 @@ static int rollout_fwd_impl(const rlsde_env* env, const rlsde_mlp* mlp, const fl
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
   int lrc = -1;
   const bool warp_path = use_warp_kernels(A, mlp->d_hidden, sm, (A.flags & RLSDE_F_STORE_PATH) != 0);
+  // ---- schedule of the thread-per-trajectory kernel (rollout_fwd.cuh)
+  // Passes per slice: the launch's tail is ~4 slices of the slowest warp; a hand-off every 8 passes costs ~3 % in steady
+  // state.  Measured at n_steps_lim = 1000, 1e6 trajectories, 24 % of them running into the limit: 24.3 / 24.5 / 24.9 /
+  // 25.4 / 27.8 ms at 4 / 8 / 16 / 32 / 128 passes, 27.8 ms without slicing -> 1/128 of the pass budget, between 8 and 128.
+  // Training rollouts (RLSDE_F_STORE_PATH) and budgets far above the typical length (the metastable configuration: mean
+  // 7e4 passes, a few trajectories near the 1e6-pass limit) run to completion instead -- their tail is the sequential
+  // length of a few very long trajectories, which round-robin slices only delay -- and hand those last trajectories over
+  // to the warp-per-trajectory kernel (RESUME mode, K1's arithmetic), which advances a lone trajectory ~5x faster.
+  {
+    const long long lim_eff = (A.flags & RLSDE_F_NOISE_INJECTED) && A.noise_steps < A.n_steps_lim ? A.noise_steps : A.n_steps_lim;
+    long long quantum = lim_eff / 128 > 128 ? 128 : (lim_eff / 128 < 8 ? 8 : lim_eff / 128);
+    if ((A.flags & RLSDE_F_STORE_PATH) || lim_eff > 16384) quantum = 0;
+    if (const char* ev = getenv("RLSDE_FWD_QUANTUM")) quantum = atoll(ev);
+    if (quantum > 0) {                                    // a power of two, at least one noise block (4 passes)
+      long long q2 = 4;
+      while (q2 < quantum && q2 < (1LL << 30)) q2 <<= 1;
+      quantum = q2;
+    }
+    A.q_quantum = (int)quantum;
+    A.q_handoff = 0;
+    if (quantum == 0 && mlp->d_hidden == WARP_H && !tr.base) A.q_handoff = 4LL * warp_path_max_k(sm);
+    if (const char* ev = getenv("RLSDE_FWD_HANDOFF")) A.q_handoff = (quantum == 0 && mlp->d_hidden == WARP_H && !tr.base) ? atoll(ev) : 0;
+  }
 #define X(D_, H_)                                                                              \
   if (env->d == D_ && mlp->d_hidden == H_)                                                     \
     lrc = (warp_path && H_ == WARP_H) ? launch_rollout_fwd_warp<D_>(params_host, nullptr, A, sm, stream) \
@@ -214,6 +238,15 @@ static int rollout_fwd_impl(const rlsde_env* env, const rlsde_mlp* mlp, const fl
   RLSDE_SHAPES(X)
 #undef X
   if (lrc != 0) return cuda_fail((cudaError_t)lrc, "rollout_fwd launch");
+  if (!warp_path && A.q_handoff > 0 && A.q_quantum == 0 && A.q_ring != nullptr) {
+    // the trajectories K1 left in the ring (none if it ran without one): one warp each, K1's arithmetic
+    lrc = -1;
+#define X(D_, H_) \
+  if (env->d == D_ && mlp->d_hidden == H_ && H_ == WARP_H) lrc = launch_rollout_fwd_warp_resume<D_>(params_host, A, sm, stream);
+    RLSDE_SHAPES(X)
+#undef X
+    if (lrc != 0) return cuda_fail((cudaError_t)lrc, "rollout_fwd resume launch");
+  }
   if (stats_dev) {
     double* partial = (double*)((char*)workspace_dev + WS_COUNTER_BYTES);
     // passes an undetected trajectory has executed: the budget, or the injected noise if that is shorter

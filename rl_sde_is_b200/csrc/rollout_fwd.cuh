@@ -84,7 +84,10 @@ struct FwdArgs {
   long long q_cap;                     // records in the ring: a power of two >= K + lanes of the grid
   int q_cap_log2;
   unsigned long long* q_ctrl;          // [0] items claimed (== counter), [1] continuation records queued, [2] trajectories completed
-  int q_quantum;                       // passes per slice
+  int q_quantum;                       // passes per slice (0: run to completion)
+  long long q_handoff;                 // > 0 (run-to-completion only): once all trajectories have been started and at most
+                                       // this many are still live, they are left in the ring for the warp-per-trajectory
+                                       // kernel, which advances a lone trajectory ~5x faster (rollout_warp.cuh, RESUME)
 };
 
 // State of an in-flight trajectory: everything a lane needs to continue it (x, accumulators, pass index).
@@ -149,7 +152,8 @@ __global__ void __launch_bounds__(128, (D == 1 ? 8 : 1)) rollout_fwd_kernel(cons
   const bool want_l2 = (D == 1) && A.policy_opt != nullptr && A.l2 != nullptr;
   const long long lim = inject ? (A.noise_steps < A.n_steps_lim ? A.noise_steps : A.n_steps_lim) : A.n_steps_lim;
   typedef ContRec<D, F64> Rec;
-  const bool sliced = A.q_ring != nullptr;
+  const bool sliced = A.q_ring != nullptr && A.q_quantum > 0;
+  const bool handoff = A.q_ring != nullptr && A.q_quantum == 0 && A.q_handoff > 0;
   Rec* const ring = reinterpret_cast<Rec*>(A.q_ring);
   // live state is kept small (the register budget of 8 blocks per SM is 64): while a lane waits for a record, `traj`
   // holds the record's index; slices end where the pass index is a multiple of the quantum (a power of two)
@@ -168,13 +172,36 @@ __global__ void __launch_bounds__(128, (D == 1 ? 8 : 1)) rollout_fwd_kernel(cons
 
   for (unsigned it = 0;; ++it) {
     if ((it & (SPB - 1)) == 0) {
-      if (sliced) {
+      if (sliced || handoff) {
         // (a) report the trajectories that completed since the last boundary
         const unsigned fm = __ballot_sync(FULL, fin);
         if (fm) {
           if (lane == __ffs(fm) - 1) atomicAdd(A.q_ctrl + 2, (unsigned long long)__popc(fm));
           fin = false;
         }
+      }
+      if (handoff && (it & (4u * SPB - 1u)) == 0) {
+        // every 4th boundary: is this the tail of the launch?  then leave the live trajectories to the latency kernel
+        const unsigned long long claimed = *reinterpret_cast<volatile unsigned long long*>(A.q_ctrl);
+        const unsigned long long completed = *reinterpret_cast<volatile unsigned long long*>(A.q_ctrl + 2);
+        if (claimed >= (unsigned long long)A.K && (unsigned long long)A.K - completed <= (unsigned long long)A.q_handoff) {
+          const unsigned live = __ballot_sync(FULL, alive);
+          if (live) {
+            unsigned long long base = 0;
+            const int leader = __ffs(live) - 1;
+            if (lane == leader) base = atomicAdd(A.q_ctrl + 1, (unsigned long long)__popc(live));
+            base = __shfl_sync(FULL, base, leader);
+            if (alive) {
+              Rec* r = ring + (base + __popc(live & ((1u << lane) - 1u)));
+              r->traj = traj; r->k = k; r->seq = 1; r->G = G; r->S = S; r->L2 = L2;
+#pragma unroll
+              for (int i = 0; i < D; ++i) r->x[i] = x[i];
+            }
+          }
+          break;
+        }
+      }
+      if (sliced) {
         // (b) slice over: append the trajectory to the FIFO
         const bool expire = alive && k != 0 && (k & qmask) == 0;   // (a resumed lane is past this check: it resumes in (d))
         const unsigned em = __ballot_sync(FULL, expire);

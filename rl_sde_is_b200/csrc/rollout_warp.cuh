@@ -86,8 +86,38 @@ __device__ __forceinline__ void warp_policy(const LaneParams<D>& P, float* slot,
   for (int k = 0; k < D; ++k) u[k] = P.b3[k] + warp_sum(P.w3[k] * h2);
 }
 
+// Same policy with K1's summation orders (rollout_fwd.cuh / common.cuh): one FMA chain per hidden unit over the inputs
+// in index order, the head as two chains over the even / odd activations added at the end.  ~70 cycles slower per pass
+// than warp_policy, but bit-identical to the thread-per-trajectory kernel, so a trajectory that K1 hands over (the last
+// long trajectories of a launch) continues exactly as K1 would have continued it.
+template <int D, bool FAST>
+__device__ __forceinline__ void warp_policy_exact(const LaneParams<D>& P, const MlpConst<D, WARP_H>& W, float* slot, int lane,
+                                                  const float (&x)[D], float (&u)[D]) {
+  float z = P.b1;
+#pragma unroll
+  for (int i = 0; i < D; ++i) z = fmaf(x[i], P.w1[i], z);
+  float all[WARP_H];
+  warp_allgather(slot, lane, tanh_scalar<FAST>(z), all);
+  float a = P.b2;
+#pragma unroll
+  for (int i = 0; i < WARP_H; ++i) a = fmaf(all[i], P.w2row[i], a);
+  warp_allgather(slot, lane, tanh_scalar<FAST>(a), all);
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    float lo = W.b3[k], hi = 0.0f;
+#pragma unroll
+    for (int j = 0; j < WARP_H; j += 2) {
+      lo = fmaf(all[j], W.W3[k][j], lo);
+      hi = fmaf(all[j + 1], W.W3[k][j + 1], hi);
+    }
+    u[k] = __fadd_rn(lo, hi);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ forward
-template <int D, bool F64, bool FAST>
+// RESUME = true: the work items are the continuation records K1 left in the ring when it handed the last live
+// trajectories of its launch over (rollout_fwd.cuh); they are continued with K1's arithmetic (warp_policy_exact).
+template <int D, bool F64, bool FAST, bool RESUME>
 __global__ void __launch_bounds__(128) rollout_fwd_warp_kernel(const __grid_constant__ MlpConst<D, WARP_H> W_param,
                                                                const MlpConst<D, WARP_H>* __restrict__ W_dev,
                                                                const __grid_constant__ FwdArgs A) {
@@ -109,15 +139,41 @@ __global__ void __launch_bounds__(128) rollout_fwd_warp_kernel(const __grid_cons
   LaneParams<D> P;
   P.load(W, lane);
 
-  for (long long traj = gw; traj < A.K; traj += n_warps) {
+  typedef ContRec<D, F64> Rec;
+  const long long n_items = RESUME ? (long long)A.q_ctrl[1] : A.K;
+  // fresh batches: static round robin (deterministic reverse-pass partials rely on nothing here, but it is free);
+  // resumed tails: lengths differ by orders of magnitude, so warps take records from a counter as they become free
+  auto next_item = [&](long long prev) -> long long {
+    if constexpr (RESUME) {
+      unsigned long long i = 0;
+      if (lane == 0) i = atomicAdd(A.q_ctrl + 3, 1ull);
+      return (long long)__shfl_sync(0xffffffffu, i, 0);
+    } else {
+      return prev < 0 ? gw : prev + n_warps;
+    }
+  };
+  for (long long item = next_item(-1); item < n_items; item = next_item(item)) {
+    long long traj = item;
+    int k_first = 0;
     real x[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) x[i] = F64 ? (real)A.x0_d[i] : (real)A.x0_f[i];
     real G = 0, S = 0, L2 = 0;
+    if constexpr (RESUME) {
+      const Rec* r = reinterpret_cast<const Rec*>(A.q_ring) + item;
+      traj = r->traj; k_first = r->k; G = r->G; S = r->S; L2 = r->L2;
+#pragma unroll
+      for (int i = 0; i < D; ++i) x[i] = r->x[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < D; ++i) x[i] = F64 ? (real)A.x0_d[i] : (real)A.x0_f[i];
+    }
     float z[NoisePlan<D>::NZ];
     long long t_out = -1;
     int ck = 0;
-    for (int k = 0; k < (int)lim; ++k) {
+    if (RESUME && store_path) {
+      const int rem = k_first % A.ckpt_every;
+      ck = rem ? A.ckpt_every - rem : 0;
+    }
+    for (int k = k_first; k < (int)lim; ++k) {
       if (!inject && (k % SPB) == 0) {
         const unsigned long long gt = (unsigned long long)(A.traj_offset + traj);
 #pragma unroll
@@ -128,10 +184,15 @@ __global__ void __launch_bounds__(128) rollout_fwd_warp_kernel(const __grid_cons
           for (int s = 0; s < 4; ++s) z[4 * q + s] = zz[s];
         }
       }
-      float xf[D], u[D], h1, h2, h1_all[WARP_H], dB[D];
+      float xf[D], u[D], dB[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) xf[i] = (float)x[i];
-      warp_policy<D, FAST>(P, slot, lane, xf, h1, h1_all, h2, u);
+      if constexpr (RESUME) {
+        warp_policy_exact<D, FAST>(P, W, slot, lane, xf, u);
+      } else {
+        float h1, h2, h1_all[WARP_H];
+        warp_policy<D, FAST>(P, slot, lane, xf, h1, h1_all, h2, u);
+      }
       if (inject) {
         const long long row = (long long)k * A.K_global + (A.traj_offset + traj);
 #pragma unroll
@@ -348,6 +409,9 @@ int launch_rollout_fwd_warp(const float* params_host, const void* W_dev, const F
 template <int D>
 int launch_rollout_bwd_warp(const float* params_host, const void* W_dev, const FwdArgs& args, float scale, float* grad,
                             float* partial, int sm_count, cudaStream_t stream);
+// continues the trajectories the thread-per-trajectory kernel left in args.q_ring (args.q_ctrl[1] records)
+template <int D>
+int launch_rollout_fwd_warp_resume(const float* params_host, const FwdArgs& args, int sm_count, cudaStream_t stream);
 // theta_dev (flat float32, state_dict order) -> MlpConst<D, WARP_H> in device memory, same rounding as the host packer
 template <int D>
 int launch_pack_mlp_const_dev(const float* theta_dev, void* W_dev, bool fast_tanh, cudaStream_t stream);

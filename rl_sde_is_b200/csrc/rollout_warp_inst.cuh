@@ -46,7 +46,7 @@ static int launch_fwd_warp_variant(const float* params_host, const void* W_dev, 
   MlpConst<D, WARP_H> W;
   if (params_host != nullptr) pack_mlp_const<D, WARP_H>(params_host, FAST, W);
   else memset(&W, 0, sizeof(W));
-  rollout_fwd_warp_kernel<D, F64, FAST><<<(unsigned)warp_grid(args.K, sm_count), 128, 0, stream>>>(
+  rollout_fwd_warp_kernel<D, F64, FAST, false><<<(unsigned)warp_grid(args.K, sm_count), 128, 0, stream>>>(
       W, params_host != nullptr ? nullptr : reinterpret_cast<const MlpConst<D, WARP_H>*>(W_dev), args);
   note_kernel_launches(1);
   return (int)cudaGetLastError();
@@ -59,6 +59,25 @@ int launch_rollout_fwd_warp(const float* params_host, const void* W_dev, const F
                        : launch_fwd_warp_variant<D, true, false>(params_host, W_dev, args, sm_count, stream);
   return fast ? launch_fwd_warp_variant<D, false, true>(params_host, W_dev, args, sm_count, stream)
               : launch_fwd_warp_variant<D, false, false>(params_host, W_dev, args, sm_count, stream);
+}
+
+template <int D, bool F64, bool FAST>
+static int launch_fwd_warp_resume_variant(const float* params_host, const FwdArgs& args, int sm_count, cudaStream_t stream) {
+  MlpConst<D, WARP_H> W;
+  pack_mlp_const<D, WARP_H>(params_host, FAST, W);
+  // the number of records is only known on the device: a full grid (16 warps per SM), warps without a record leave at once
+  rollout_fwd_warp_kernel<D, F64, FAST, true><<<(unsigned)(sm_count * 4), 128, 0, stream>>>(W, nullptr, args);
+  note_kernel_launches(1);
+  return (int)cudaGetLastError();
+}
+
+template <int D>
+int launch_rollout_fwd_warp_resume(const float* params_host, const FwdArgs& args, int sm_count, cudaStream_t stream) {
+  const bool f64 = (args.flags & RLSDE_F_STATE_F64) != 0, fast = (args.flags & RLSDE_F_TANH_FAST) != 0;
+  if (f64) return fast ? launch_fwd_warp_resume_variant<D, true, true>(params_host, args, sm_count, stream)
+                       : launch_fwd_warp_resume_variant<D, true, false>(params_host, args, sm_count, stream);
+  return fast ? launch_fwd_warp_resume_variant<D, false, true>(params_host, args, sm_count, stream)
+              : launch_fwd_warp_resume_variant<D, false, false>(params_host, args, sm_count, stream);
 }
 
 template <int D, bool FAST>
@@ -92,4 +111,5 @@ int launch_rollout_bwd_warp(const float* params_host, const void* W_dev, const F
   template int rlsde::launch_rollout_fwd_warp<D>(const float*, const void*, const rlsde::FwdArgs&, int, cudaStream_t);     \
   template int rlsde::launch_rollout_bwd_warp<D>(const float*, const void*, const rlsde::FwdArgs&, float, float*, float*, \
                                                  int, cudaStream_t);                                                       \
-  template int rlsde::launch_pack_mlp_const_dev<D>(const float*, void*, bool, cudaStream_t);
+  template int rlsde::launch_pack_mlp_const_dev<D>(const float*, void*, bool, cudaStream_t);                              \
+  template int rlsde::launch_rollout_fwd_warp_resume<D>(const float*, const rlsde::FwdArgs&, int, cudaStream_t);

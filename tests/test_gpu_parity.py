@@ -713,3 +713,41 @@ def test_device_resident_training_loop_matches_host_loop():
     m1 = reinforce(env, device_loop=True, **{**kw, "n_iterations": 1})["model"]
     for (k, a), (_, b) in zip(m0.named_parameters(), m1.named_parameters()):
         np.testing.assert_allclose(b.detach().numpy(), a.detach().numpy(), rtol=0, atol=3e-7, err_msg=k)
+
+
+@pytest.mark.parametrize("d,f64", [(1, False), (1, True), (2, False)])
+def test_tail_handoff_to_warp_kernel_is_bit_identical(monkeypatch, d, f64):
+    """Run-to-completion launches leave their last live trajectories to the warp-per-trajectory kernel, which continues
+    them with K1's summation orders: outputs (incl. the l2 error and the path checkpoints) equal the launch without the
+    hand-off bit for bit."""
+    from rl_sde_is_b200 import _lib as L, rollout as R
+    from rl_sde_is_b200.models import DeterministicPolicy
+    env = _make_env(d, 1.0, 1.0, 0.005)
+    torch.manual_seed(21)
+    model = DeterministicPolicy(d, d, [32, 32], nn.Tanh())
+    model.policy[4].bias.data.fill_(0.6 if d == 1 else 1.6)
+    params = R.flat_parameters(model).detach().numpy()
+    rule = L.HIT_X0_IN_LB_RB if (f64 and d == 1) else L.HIT_ALL_GE_LB
+    env_c, mlp_c = R.env_struct(env, rule), L.make_mlp(d, 32)
+    K = 30000
+    pol = np.linspace(-1, 1, 81) if d == 1 else None
+    grid = (-2.0, 2.0, 0.05) if d == 1 else None
+    outs = []
+    for h in ("0", "4000", "40000"):                 # no hand-off / near the end / almost from the start
+        monkeypatch.setenv("RLSDE_FWD_QUANTUM", "0")
+        monkeypatch.setenv("RLSDE_FWD_HANDOFF", h)
+        o = R.rollout_forward(env_c, mlp_c, params, K, seed=77, n_steps_lim=20000, state_f64=f64, want_logw=True,
+                              policy_opt=pol, grid=grid, store_path=not f64, ckpt_every=2)
+        outs.append(o)
+    T = outs[0].T.cpu().numpy()
+    assert (T >= 0).all() and T.max() > 5 * np.median(T)         # a long tail: the hand-off has something to do
+    for o in outs[1:]:
+        assert torch.equal(o.G, outs[0].G) and torch.equal(o.S, outs[0].S) and torch.equal(o.T, outs[0].T)
+        assert torch.equal(o.logw, outs[0].logw)
+        if d == 1:
+            assert torch.equal(o.l2, outs[0].l2)
+        if not f64:
+            n_ck = T // 2 + 1
+            mask = torch.as_tensor(np.arange(o.path.shape[1])[None, :] < n_ck[:, None], device=o.path.device)
+            for i in range(d):
+                assert torch.equal(o.path[..., i][mask], outs[0].path[..., i][mask])
