@@ -178,9 +178,14 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly ONE line, the JSON record: everything libraries print on file descriptor 1 meanwhile (NCCL's
+    # version banner comes from C code, whatever NCCL_DEBUG or /etc/nccl.conf say) is sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: one JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
@@ -306,7 +311,8 @@ def run_gpu_arm(args):
         "gpu_launches": gpu_launches,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "extra": extra,
     }
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0

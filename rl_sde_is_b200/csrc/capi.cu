@@ -212,14 +212,16 @@ static int rollout_fwd_impl(const rlsde_env* env, const rlsde_mlp* mlp, const fl
   // Passes per slice: the launch's tail is ~4 slices of the slowest warp; a hand-off every 8 passes costs ~3 % in steady
   // state.  Measured at n_steps_lim = 1000, 1e6 trajectories, 24 % of them running into the limit: 24.3 / 24.5 / 24.9 /
   // 25.4 / 27.8 ms at 4 / 8 / 16 / 32 / 128 passes, 27.8 ms without slicing -> 1/128 of the pass budget, between 8 and 128.
-  // Training rollouts (RLSDE_F_STORE_PATH) and budgets far above the typical length (the metastable configuration: mean
-  // 7e4 passes, a few trajectories near the 1e6-pass limit) run to completion instead -- their tail is the sequential
-  // length of a few very long trajectories, which round-robin slices only delay -- and hand those last trajectories over
-  // to the warp-per-trajectory kernel (RESUME mode, K1's arithmetic), which advances a lone trajectory ~5x faster.
+  // Training rollouts (RLSDE_F_STORE_PATH) and generous budgets (> 4096 passes: budgets meant as "no limit", e.g. the
+  // metastable configuration with mean 7e4 passes and a few trajectories near the 1e6-pass limit) run to completion
+  // instead -- their tail is the sequential length of a few very long trajectories, which round-robin slices only delay
+  // (8e6 trajectories on 8 GPUs: 5.96 s unsliced, 6.36 s sliced) -- and hand those last trajectories over to the
+  // warp-per-trajectory kernel (RESUME mode, K1's arithmetic), which advances a lone trajectory ~5x faster
+  // (1e6 metastable trajectories on one GPU: 5.68 -> 4.14 s; training forward at K = 4e5: 21.5 -> 13.9 ms).
   {
     const long long lim_eff = (A.flags & RLSDE_F_NOISE_INJECTED) && A.noise_steps < A.n_steps_lim ? A.noise_steps : A.n_steps_lim;
     long long quantum = lim_eff / 128 > 128 ? 128 : (lim_eff / 128 < 8 ? 8 : lim_eff / 128);
-    if ((A.flags & RLSDE_F_STORE_PATH) || lim_eff > 16384) quantum = 0;
+    if ((A.flags & RLSDE_F_STORE_PATH) || lim_eff > 4096) quantum = 0;
     if (const char* ev = getenv("RLSDE_FWD_QUANTUM")) quantum = atoll(ev);
     if (quantum > 0) {                                    // a power of two, at least one noise block (4 passes)
       long long q2 = 4;
