@@ -308,10 +308,37 @@ int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
   float* partial = (float*)((char*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES + WS_POLICY_BYTES);
   int lrc = -1;
   const bool warp_path = use_warp_kernels(A, mlp->d_hidden, sm, true);
+  // Large batches with a length-sorted order: the reverse pass of a trajectory is sequential, and K2 walks a lone
+  // trajectory at ~12 us per pass -- the longest few thousand trajectories, not the total work, set its run time (K = 4e5,
+  // longest 3 900 passes: 47 ms for ~28 ms of throughput work).  They go to the warp-per-trajectory kernel instead
+  // (~0.5 us per pass), the bulk stays in K2; the two gradients are added in a fixed order.  The split depends on the
+  // sorted lengths only, so the result is deterministic.
+  long long n_long = 0;
+  if (!warp_path && order_dev && A.ckpt_every == 1 && mlp->d_hidden == WARP_H && A.K > (long long)sm * 128) {
+    // measured (K = 4e5, d = 1): 46.2 / 36.7 / 36.7 / 37.5 / 41.9 ms at 0 / 2 368 / 4 736 / 9 472 / 25 000 long trajectories
+    n_long = A.K / 16 < warp_path_max_k(sm) ? A.K / 16 : warp_path_max_k(sm);
+    if (const char* ev = getenv("RLSDE_BWD_WARP_SHARE")) n_long = atoll(ev) < A.K ? atoll(ev) : A.K;
+    if (n_long < 0) n_long = 0;
+  }
+  FwdArgs Abulk = A;
+  if (n_long > 0) {
+    FwdArgs Along = A;
+    Along.K = n_long;
+    Abulk.order = A.order + n_long;
+    Abulk.K = A.K - n_long;
+    Abulk.grad_accumulate = 1;
+#define X(D_, H_)                                                                                                   \
+  if (env->d == D_ && mlp->d_hidden == H_ && H_ == WARP_H)                                                          \
+    lrc = launch_rollout_bwd_warp<D_>(params_host, nullptr, Along, (float)loss_scale, grad_dev, partial, sm, stream);
+    RLSDE_SHAPES(X)
+#undef X
+    if (lrc != 0) return cuda_fail((cudaError_t)lrc, "rollout_bwd (long trajectories) launch");
+    lrc = Abulk.K > 0 ? -1 : 0;
+  }
 #define X(D_, H_)                                                                                                          \
-  if (env->d == D_ && mlp->d_hidden == H_)                                                                                 \
-    lrc = (warp_path && H_ == WARP_H) ? launch_rollout_bwd_warp<D_>(params_host, nullptr, A, (float)loss_scale, grad_dev, partial, sm, stream) \
-                                      : launch_rollout_bwd<D_, H_>(params_host, A, (float)loss_scale, grad_dev, partial, sm, stream);
+  if (env->d == D_ && mlp->d_hidden == H_ && Abulk.K > 0)                                                                  \
+    lrc = (warp_path && H_ == WARP_H) ? launch_rollout_bwd_warp<D_>(params_host, nullptr, Abulk, (float)loss_scale, grad_dev, partial, sm, stream) \
+                                      : launch_rollout_bwd<D_, H_>(params_host, Abulk, (float)loss_scale, grad_dev, partial, sm, stream);
   RLSDE_SHAPES(X)
 #undef X
   if (lrc != 0) return cuda_fail((cudaError_t)lrc, "rollout_bwd launch");

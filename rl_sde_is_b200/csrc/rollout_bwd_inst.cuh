@@ -4,13 +4,15 @@
 
 namespace rlsde {
 
-// grad[p] = scale * sum_w partial[w][p], warps in index order
-static __global__ void bwd_reduce_kernel(const float* __restrict__ partial, int n_warps, int P, float scale, float* __restrict__ grad) {
+// grad[p] (+)= scale * sum_w partial[w][p], warps in index order
+static __global__ void bwd_reduce_kernel(const float* __restrict__ partial, int n_warps, int P, float scale, float* __restrict__ grad,
+                                         int accumulate) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   double acc = 0.0;
   for (int w = 0; w < n_warps; ++w) acc += (double)partial[(long long)w * P + p];
-  grad[p] = (float)(acc * (double)scale);
+  const float g = (float)(acc * (double)scale);
+  grad[p] = accumulate ? grad[p] + g : g;
 }
 
 template <int D, int H, bool FAST>
@@ -45,7 +47,7 @@ static int launch_bwd_variant(const float* params_host, const FwdArgs& args, flo
   kern<<<(unsigned)grid, block, smem, stream>>>(W, args, partial);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
-  bwd_reduce_kernel<<<(P + 127) / 128, 128, 0, stream>>>(partial, (int)n_warps, P, scale, grad);
+  bwd_reduce_kernel<<<(P + 127) / 128, 128, 0, stream>>>(partial, (int)n_warps, P, scale, grad, args.grad_accumulate);
   note_kernel_launches(2);
   return (int)cudaGetLastError();
 }

@@ -71,6 +71,7 @@ struct FwdArgs {
   float* path;
   unsigned long long* counter;   // work counter of THIS launch (zeroed by the host wrapper)
   const long long* order;        // reverse pass: processing order of the trajectories (or nullptr = identity)
+  int grad_accumulate;           // reverse pass: add this launch's gradient to grad instead of overwriting it
   // ---- transition stream (replay-buffer sampler, approximate_methods.py:513-545): trajectory `t` writes the tuple of
   //      its pass k at slot tr_base[t] + k of the five arrays below.  nullptr = no stream.
   const long long* tr_base;

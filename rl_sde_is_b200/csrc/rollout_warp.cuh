@@ -323,7 +323,9 @@ __global__ void __launch_bounds__(128) rollout_bwd_warp_kernel(const __grid_cons
   for (int i = 0; i < D; ++i) { gW1[i] = 0.f; gW3[i] = 0.f; gb3[i] = 0.f; }
   NoiseCache<D> nc;
 
-  for (long long traj = gw; traj < A.K; traj += n_warps) {
+  // static round robin over the (optionally length-sorted) list: deterministic per-warp partial sums
+  for (long long item = gw; item < A.K; item += n_warps) {
+    const long long traj = A.order ? A.order[item] : item;
     const int kstar = A.T[traj];
     if (kstar < 0) continue;
     const float Gk = ((const float*)A.G)[traj];

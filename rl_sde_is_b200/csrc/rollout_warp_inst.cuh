@@ -92,7 +92,7 @@ static int launch_bwd_warp_variant(const float* params_host, const void* W_dev, 
       W, params_host != nullptr ? nullptr : reinterpret_cast<const MlpConst<D, WARP_H>*>(W_dev), args, partial);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
-  bwd_reduce_kernel<<<(P + 127) / 128, 128, 0, stream>>>(partial, (int)(grid * 4), P, scale, grad);
+  bwd_reduce_kernel<<<(P + 127) / 128, 128, 0, stream>>>(partial, (int)(grid * 4), P, scale, grad, args.grad_accumulate);
   note_kernel_launches(2);
   return (int)cudaGetLastError();
 }

@@ -751,3 +751,31 @@ def test_tail_handoff_to_warp_kernel_is_bit_identical(monkeypatch, d, f64):
             mask = torch.as_tensor(np.arange(o.path.shape[1])[None, :] < n_ck[:, None], device=o.path.device)
             for i in range(d):
                 assert torch.equal(o.path[..., i][mask], outs[0].path[..., i][mask])
+
+
+def test_reverse_pass_split_between_kernel_families(monkeypatch):
+    """Large batches: the longest trajectories of the length-sorted order are differentiated by the warp-per-trajectory
+    kernel, the bulk by the thread-per-trajectory kernel, and the two gradients are added.  Any split gives the same
+    gradient to float32 summation rounding, and the same split gives the same bits."""
+    from rl_sde_is_b200 import _lib as L, rollout as R
+    from rl_sde_is_b200.models import DeterministicPolicy
+    env = _make_env(1, 1.0, 1.0, 0.005)
+    torch.manual_seed(5)
+    model = DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    model.policy[4].bias.data.fill_(0.7)
+    params = R.flat_parameters(model).detach().numpy()
+    env_c, mlp_c = R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(1, 32)
+    K = 40000
+    out = R.rollout_forward(env_c, mlp_c, params, K, seed=8, n_steps_lim=20000, store_path=True, ckpt_every=1, want_logw=False)
+    grads = {}
+    for share in ("0", "1000", "2500", "40000"):
+        monkeypatch.setenv("RLSDE_BWD_WARP_SHARE", share)
+        grads[share] = R.rollout_backward(env_c, mlp_c, params, out, 1.0 / K).cpu().numpy()
+    monkeypatch.delenv("RLSDE_BWD_WARP_SHARE")
+    default = R.rollout_backward(env_c, mlp_c, params, out, 1.0 / K).cpu().numpy()        # min(K / 16, 16 x SMs) long trajectories
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    monkeypatch.setenv("RLSDE_BWD_WARP_SHARE", str(min(K // 16, 16 * n_sm)))
+    assert np.array_equal(default, R.rollout_backward(env_c, mlp_c, params, out, 1.0 / K).cpu().numpy())
+    scale = np.abs(grads["0"]).max()
+    for share in ("1000", "2500", "40000"):
+        np.testing.assert_allclose(grads[share], grads["0"], rtol=0, atol=2e-5 * scale, err_msg=share)
