@@ -352,7 +352,27 @@ def secondary_measurements(dev):
                 ts.append(a.elapsed_time(b) / reps)
             ms = float(min(ts[1:]))
             tab[name] = {"ms": ms, "GBps": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / float(peaks.get("hbm_gbs", 6536.7))}
-        del bufs
+        # one Bellman sweep over the resident tensor: HBM-read bound, same timing method
+        from rl_sde_is_b200.dynamic_programming import compute_r_table
+        from rl_sde_is_b200.tabular_dp_sweeps import DeviceTables
+        T = DeviceTables(env, compute_r_table(env, device=dev, device_out=True), bufs[0])
+        v = torch.full((env.n_states,), -1.0, dtype=torch.float64, device=dev)
+        ts = []
+        for trial in range(3):
+            T.sweep(v, 1.0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(16):
+                T.sweep(v, 1.0)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) / 16)
+        ms = float(min(ts[1:]))
+        out["dp_sweep_config2"] = {"bytes": nbytes, "ms": ms, "GBps": nbytes / ms / 1e6,
+                                   "frac_of_hbm_peak": nbytes / ms / 1e6 / float(peaks.get("hbm_gbs", 6536.7)),
+                                   "note": "values = R + (1 - d) gamma P^T v over the 773 MB tensor (q/v/policy updates of "
+                                           "tabular_dp_*_iteration.py); reference ~0.3 s per sweep in NumPy"}
+        del T, bufs
         out["tables_config2"] = {"bytes": nbytes, **tab, "reference_cpu_s": 55.3,
                                  "note": "P (401, 401, 601) float64 device-resident; roofline = HBM write, peak = MEASURED_PEAKS hbm_gbs; "
                                          "CUDA events around 8 back-to-back builds into alternating outputs"}
