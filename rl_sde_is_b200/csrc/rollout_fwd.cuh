@@ -136,10 +136,11 @@ struct NoisePlan {
   static constexpr int NZ = 4 * BPP;
 };
 
-// d = 1 is held to 64 registers (8 blocks per SM: ptxas finds a spill-free allocation under the bound, but settles at
-// 67 without it); the wider shapes would spill under the same bound and are left to the default heuristics.
+// Register budgets.  Left alone, ptxas settles at 67 registers for d = 1 and at ~250 for the wider shapes (2 blocks per
+// SM: two warps per scheduler, every FFMA2 waiting for its LDCU.128), although spill-free allocations exist at 64
+// (d = 1: 8 blocks per SM), <= 102 (d = 2..4: 5 blocks) and <= 128 (d = 10: 4 blocks) -- it finds them when asked.
 template <int D, int H, bool F64, bool FAST>
-__global__ void __launch_bounds__(128, (D == 1 ? 8 : 1)) rollout_fwd_kernel(const __grid_constant__ MlpConst<D, H> W,
+__global__ void __launch_bounds__(128, (D == 1 ? 8 : (D <= 4 ? 5 : 4))) rollout_fwd_kernel(const __grid_constant__ MlpConst<D, H> W,
                                                           const __grid_constant__ FwdArgs A) {
   typedef typename RealT<F64>::type real;
   constexpr int SPB = NoisePlan<D>::SPB;
