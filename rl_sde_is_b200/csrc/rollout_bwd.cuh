@@ -56,9 +56,10 @@ inline size_t bwd_workspace_bytes() { return (size_t)BWD_MAX_WARPS * BWD_MAX_PAR
 //   PAD = false: XOR swizzle at float4 granularity (no extra memory, ~1 450 integer instructions per pass for addresses);
 //   PAD = true:  rows padded to H + 4 floats (plain addresses).
 // Measured (tools/bench_train.py): at d = 1, where the kernel runs 4 blocks per SM, the padded layout is 19 % faster
-// (57.7 -> 46.8 ms: with four warps per scheduler the instruction count is what limits); at 2 blocks per SM (d >= 2) the
-// swizzle is 3-5 % faster (the address arithmetic fills issue slots that would idle anyway).
-constexpr bool bwd_tiles_padded(int D) { return D == 1; }
+// (57.7 -> 46.8 ms: with four warps per scheduler the instruction count is what limits), at d = 2..4 with 3 blocks per SM
+// 14 % faster; at 2 blocks per SM (d = 10) the swizzle is 3-5 % faster (the address arithmetic fills issue slots that
+// would idle anyway).
+constexpr bool bwd_tiles_padded(int D) { return D <= 4; }
 template <int H, bool PAD>
 __device__ __forceinline__ int swz(int row, int col) {
   if constexpr (PAD) return row * (H + 4) + col;
@@ -127,8 +128,9 @@ __device__ __forceinline__ void em_step_f32(const FwdArgs& A, float (&x)[D], con
 // Resident blocks per SM the register allocation aims for.  Measured on B200 (K = 4e5 / 2e5, tools/bench_train.py):
 //   d = 1:  2 blocks (210 registers) 63.3 ms, 3 blocks (168) 61.4 ms, 4 blocks (128, 16 B of spills) 58.2 ms
 //   d = 10: 2 blocks 22.4 ms, 3 blocks 27.4 ms, 4 blocks 29.8 ms (the wider head spills)
+//   d = 2 (K = 2e5): 2 blocks + swizzled tiles 8.0 ms, 3 blocks + padded tiles 7.0 ms; d = 10: 20.3 vs 20.9 ms
 #ifndef RLSDE_BWD_MIN_BLOCKS
-#define RLSDE_BWD_MIN_BLOCKS(D) ((D) == 1 ? 4 : 2)
+#define RLSDE_BWD_MIN_BLOCKS(D) ((D) == 1 ? 4 : ((D) <= 4 ? 3 : 2))
 #endif
 
 // Per-warp partial gradient layout = state_dict order: W1 (H,D), b1 (H), W2 (H,H), b2 (H), W3 (D,H), b3 (D)
