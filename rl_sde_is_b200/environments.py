@@ -11,9 +11,11 @@ What runs where:
     through ``rlsde_env_step`` -- API completeness only; the fast path is the whole-rollout kernel.
   * grids, index sets, action bounds (environments.py:250-360): NumPy on the host, called once
     ("stay in Python/NumPy; pass resulting arrays to the kernels").
-  * ``step_vectorized_stopped`` (environments.py:164-199) is not provided: it has no caller in the reference and
-    raises a broadcasting ValueError there (``f(states[idx])`` has shape (n,) against (n, 1) action terms), so there
-    is no behaviour to reproduce.
+  * ``step_vectorized_stopped`` (environments.py:164-199; environments_2d.py:155-182) has no caller in the reference and
+    raises a broadcasting ValueError there for every input (``f(states[idx])`` has shape (n,) against (n, 1) action
+    terms; verified in 1-D and 2-D).  It is provided with the semantics its body spells out -- only the lanes in ``idx``
+    move, ``done`` is tested on the NEXT state with ``x >= lb``, rewards are the running cost of the moved lanes and 0
+    elsewhere -- through the same single-pass kernel as ``step``.
   * ``DoubleWellStoppingTimeND`` generalises the 2-D class to any d <= 16 (the d = 10 config has no
     reference environment; semantics follow environments_2d.py:15,50-61,114-121,184-205).
 """
@@ -118,6 +120,22 @@ class _DoubleWellBase:
         rule = L.HIT_X0_IN_LB_RB if self.d == 1 else L.HIT_ALL_GE_LB
         nxt, rew, done, db = self._device_step(state, action, True, rule, reward_type, dbt)
         return nxt.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy(), db.cpu().numpy()
+
+    def step_vectorized_stopped(self, states, actions, idx, dbt=None):
+        """Masked pass (environments.py:164-199): lanes ``idx`` take one Euler-Maruyama step, the others keep their state.
+        Returns ``(next_states (K, d) f64, rewards (K, 1) f64, done (K, d) bool on the next states, dbt (n, d) f32)``."""
+        states = np.asarray(states)
+        idx = np.asarray(idx, dtype=np.int64).reshape(-1)
+        next_states = states.astype(np.float64, copy=True)
+        rewards = np.zeros((states.shape[0], 1))
+        db = np.zeros((0, self.d), dtype=np.float32)
+        if idx.size:
+            nxt, rew, _, db = self._device_step(states[idx], np.asarray(actions)[idx], True, L.HIT_ALL_GE_LB,
+                                                "state-action-next-state", dbt)
+            next_states[idx] = nxt.cpu().numpy()
+            rewards[idx, 0] = rew.cpu().numpy()
+            db = db.cpu().numpy()
+        return next_states, rewards, next_states >= self.lb, db
 
     def step_torch(self, state, action, reward_type="state-action", dbt=None):
         """Torch-path pass (environments.py:201-226): float32; results come back on the input's device."""

@@ -779,3 +779,24 @@ def test_reverse_pass_split_between_kernel_families(monkeypatch):
     scale = np.abs(grads["0"]).max()
     for share in ("1000", "2500", "40000"):
         np.testing.assert_allclose(grads[share], grads["0"], rtol=0, atol=2e-5 * scale, err_msg=share)
+
+
+@pytest.mark.parametrize("d", [1, 2])
+def test_step_vectorized_stopped_intended_semantics(golden, d):
+    """environments.py:164-199 raises a broadcasting error in the reference for every input; the port implements what its
+    body spells out: only lanes ``idx`` move (NumPy arithmetic of ``step``), done on the next state, running-cost rewards."""
+    g = golden("env_step")
+    env = _make_env(d, 1.0, 1.0, 0.005)
+    states, actions = g[f"states{d}"], g[f"actions{d}"]
+    idx = np.array([0, 3, 4, 10, 63])
+    dbt = (0.07 * np.arange(1, 1 + idx.size * d, dtype=np.float32)).reshape(idx.size, d) * (-1) ** np.arange(idx.size)[:, None]
+    nxt, rew, done, db = env.step_vectorized_stopped(states, actions, idx, dbt=dbt.astype(np.float32))
+    want_n, want_r, _ = ref.env_step_numpy(d, 1.0, 1.0, 0.005, states[idx], actions[idx], dbt.astype(np.float32),
+                                           reward_type="state-action-next-state")
+    keep = np.setdiff1d(np.arange(states.shape[0]), idx)
+    assert nxt.dtype == np.float64 and nxt.shape == states.shape and rew.shape == (states.shape[0], 1)
+    assert np.array_equal(nxt[idx], want_n) and np.array_equal(nxt[keep], states[keep].astype(np.float64))
+    assert np.array_equal(rew[idx, 0], want_r) and np.all(rew[keep] == 0.0)
+    assert np.array_equal(done, nxt >= 1.0) and np.array_equal(db, dbt.astype(np.float32))
+    empty = env.step_vectorized_stopped(states, actions, np.array([], dtype=int))
+    assert np.array_equal(empty[0], states.astype(np.float64)) and empty[3].shape == (0, d)
