@@ -54,9 +54,18 @@ struct LaneParams {
   float w2row[WARP_H], b2;    // row `lane` of W2: weights into hidden unit `lane`
   float w3[D];                // column `lane` of W3
   float b3[D];                // head bias (uniform)
+  // narrow heads: the whole of W3 in every lane, so that each lane can sum the head itself (see warp_policy)
+  static constexpr bool HEAD_LOCAL = D <= 2;
+  float w3all[HEAD_LOCAL ? D : 1][WARP_H];
   __device__ __forceinline__ void load(const MlpConst<D, WARP_H>& W, int lane) {   // W: kernel parameter or device memory
 #pragma unroll
     for (int i = 0; i < D; ++i) { w1[i] = W.W1t[i][lane]; w3[i] = W.W3[i][lane]; b3[i] = W.b3[i]; pin(w1[i]); pin(w3[i]); }
+    if constexpr (HEAD_LOCAL) {
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < WARP_H; ++j) { w3all[i][j] = W.W3[i][j]; pin(w3all[i][j]); }
+    }
     b1 = W.b1[lane]; pin(b1);
     b2 = W.b2[lane]; pin(b2);
 #pragma unroll
@@ -82,8 +91,27 @@ __device__ __forceinline__ void warp_policy(const LaneParams<D>& P, float* slot,
     a3 = fmaf(h1_all[i + 3], P.w2row[i + 3], a3);
   }
   h2 = tanh_scalar<FAST>((a0 + a1) + (a2 + a3));
+  if constexpr (LaneParams<D>::HEAD_LOCAL) {
+    // head: a second exchange through shared memory and four FMA chains per lane (~100 cycles) instead of a five-level
+    // shuffle butterfly (~150 cycles) on the critical path of the pass
+    float h2_all[WARP_H];
+    warp_allgather(slot, lane, h2, h2_all);
 #pragma unroll
-  for (int k = 0; k < D; ++k) u[k] = P.b3[k] + warp_sum(P.w3[k] * h2);
+    for (int k = 0; k < D; ++k) {
+      float c0 = P.b3[k], c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < WARP_H; j += 4) {
+        c0 = fmaf(h2_all[j], P.w3all[k][j], c0);
+        c1 = fmaf(h2_all[j + 1], P.w3all[k][j + 1], c1);
+        c2 = fmaf(h2_all[j + 2], P.w3all[k][j + 2], c2);
+        c3 = fmaf(h2_all[j + 3], P.w3all[k][j + 3], c3);
+      }
+      u[k] = (c0 + c1) + (c2 + c3);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < D; ++k) u[k] = P.b3[k] + warp_sum(P.w3[k] * h2);
+  }
 }
 
 // Same policy with K1's summation orders (rollout_fwd.cuh / common.cuh): one FMA chain per hidden unit over the inputs
@@ -118,7 +146,7 @@ __device__ __forceinline__ void warp_policy_exact(const LaneParams<D>& P, const 
 // RESUME = true: the work items are the continuation records K1 left in the ring when it handed the last live
 // trajectories of its launch over (rollout_fwd.cuh); they are continued with K1's arithmetic (warp_policy_exact).
 template <int D, bool F64, bool FAST, bool RESUME>
-__global__ void __launch_bounds__(128) rollout_fwd_warp_kernel(const __grid_constant__ MlpConst<D, WARP_H> W_param,
+__global__ void __launch_bounds__(128, (D <= 2 ? 4 : 1)) rollout_fwd_warp_kernel(const __grid_constant__ MlpConst<D, WARP_H> W_param,
                                                                const MlpConst<D, WARP_H>* __restrict__ W_dev,
                                                                const __grid_constant__ FwdArgs A) {
   // the policy comes by value (host parameters) or, for the device-resident training loop, from device memory
