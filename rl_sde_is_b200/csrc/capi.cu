@@ -208,30 +208,34 @@ static int rollout_fwd_impl(const rlsde_env* env, const rlsde_mlp* mlp, const fl
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
   int lrc = -1;
   const bool warp_path = use_warp_kernels(A, mlp->d_hidden, sm, (A.flags & RLSDE_F_STORE_PATH) != 0);
-  // ---- schedule of the thread-per-trajectory kernel (rollout_fwd.cuh)
-  // Passes per slice: the launch's tail is ~4 slices of the slowest warp; a hand-off every 8 passes costs ~3 % in steady
-  // state.  Measured at n_steps_lim = 1000, 1e6 trajectories, 24 % of them running into the limit: 24.3 / 24.5 / 24.9 /
-  // 25.4 / 27.8 ms at 4 / 8 / 16 / 32 / 128 passes, 27.8 ms without slicing -> 1/128 of the pass budget, between 8 and 128.
-  // Training rollouts (RLSDE_F_STORE_PATH) and generous budgets (> 4096 passes: budgets meant as "no limit", e.g. the
-  // metastable configuration with mean 7e4 passes and a few trajectories near the 1e6-pass limit) run to completion
-  // instead -- their tail is the sequential length of a few very long trajectories, which round-robin slices only delay
-  // (8e6 trajectories on 8 GPUs: 5.96 s unsliced, 6.36 s sliced) -- and hand those last trajectories over to the
-  // warp-per-trajectory kernel (RESUME mode, K1's arithmetic), which advances a lone trajectory ~5x faster
-  // (1e6 metastable trajectories on one GPU: 5.68 -> 4.14 s; training forward at K = 4e5: 21.5 -> 13.9 ms).
+  // ---- schedule of the thread-per-trajectory kernel (rollout_fwd.cuh).  Two ways to deal with the tail of a launch:
+  //  * time slices (FIFO of continuation records, breadth-first): right when many trajectories run into the pass budget
+  //    -- the bench workload, 24 % of them: 24.5 ms against 27.8 ms; passes per slice = 1/128 of the budget, between 8 and
+  //    128 (24.3 / 24.5 / 24.9 / 25.4 / 27.8 ms at 4 / 8 / 16 / 32 / 128) -- but 3-13 % slower in steady state;
+  //  * run to completion and hand the last live trajectories to the warp-per-trajectory kernel (RESUME mode, K1's
+  //    arithmetic, ~5x faster on a lone trajectory): right when the tail is a few very long trajectories (metastable
+  //    configuration 5.68 -> 4.14 s, training forward 21.5 -> 13.9 ms, d = 2 test rollouts 16.6 -> 14.5 ms).
+  // Which one applies depends on the length distribution, which the launch only learns as it goes: it starts running to
+  // completion and switches to time slices as soon as 5 % of the completed trajectories have run into the budget
+  // (q_adaptive).  RLSDE_FWD_QUANTUM forces one or the other (0 = run to completion + hand-off, n = n-pass slices).
   {
     const long long lim_eff = (A.flags & RLSDE_F_NOISE_INJECTED) && A.noise_steps < A.n_steps_lim ? A.noise_steps : A.n_steps_lim;
     long long quantum = lim_eff / 128 > 128 ? 128 : (lim_eff / 128 < 8 ? 8 : lim_eff / 128);
-    if ((A.flags & RLSDE_F_STORE_PATH) || lim_eff > 4096) quantum = 0;
-    if (const char* ev = getenv("RLSDE_FWD_QUANTUM")) quantum = atoll(ev);
+    const bool can_hand_off = mlp->d_hidden == WARP_H && !tr.base;     // the latency kernel has no transition stream
+    A.q_adaptive = can_hand_off ? 1 : 0;
+    if (!can_hand_off && lim_eff > 4096) quantum = 0;
+    if (const char* ev = getenv("RLSDE_FWD_QUANTUM")) { quantum = atoll(ev); A.q_adaptive = 0; }
     if (quantum > 0) {                                    // a power of two, at least one noise block (4 passes)
       long long q2 = 4;
       while (q2 < quantum && q2 < (1LL << 30)) q2 <<= 1;
       quantum = q2;
     }
     A.q_quantum = (int)quantum;
-    A.q_handoff = 0;
-    if (quantum == 0 && mlp->d_hidden == WARP_H && !tr.base) A.q_handoff = 4LL * warp_path_max_k(sm);
-    if (const char* ev = getenv("RLSDE_FWD_HANDOFF")) A.q_handoff = (quantum == 0 && mlp->d_hidden == WARP_H && !tr.base) ? atoll(ev) : 0;
+    A.q_handoff = (can_hand_off && (quantum == 0 || A.q_adaptive)) ? 4LL * warp_path_max_k(sm) : 0;
+    if (const char* ev = getenv("RLSDE_FWD_HANDOFF")) {
+      if (A.q_handoff > 0) A.q_handoff = atoll(ev);
+      if (A.q_handoff <= 0) { A.q_handoff = 0; A.q_adaptive = 0; }
+    }
   }
 #define X(D_, H_)                                                                              \
   if (env->d == D_ && mlp->d_hidden == H_)                                                     \
@@ -240,7 +244,7 @@ static int rollout_fwd_impl(const rlsde_env* env, const rlsde_mlp* mlp, const fl
   RLSDE_SHAPES(X)
 #undef X
   if (lrc != 0) return cuda_fail((cudaError_t)lrc, "rollout_fwd launch");
-  if (!warp_path && A.q_handoff > 0 && A.q_quantum == 0 && A.q_ring != nullptr) {
+  if (!warp_path && A.q_handoff > 0 && (A.q_quantum == 0 || A.q_adaptive) && A.q_ring != nullptr) {
     // the trajectories K1 left in the ring (none if it ran without one): one warp each, K1's arithmetic
     lrc = -1;
 #define X(D_, H_) \

@@ -84,8 +84,13 @@ struct FwdArgs {
   unsigned char* q_ring;               // ring of ContRec<D, F64> records, all-zero at launch
   long long q_cap;                     // records in the ring: a power of two >= K + lanes of the grid
   int q_cap_log2;
-  unsigned long long* q_ctrl;          // [0] items claimed (== counter), [1] continuation records queued, [2] trajectories completed
+  unsigned long long* q_ctrl;          // [0] items claimed (== counter), [1] continuation records queued, [2] trajectories
+                                       // completed, [3] records taken by the resume kernel, [4] trajectories that ran into
+                                       // the pass budget, [5] tail strategy of an adaptive launch
   int q_quantum;                       // passes per slice (0: run to completion)
+  int q_adaptive;                      // 1: start run-to-completion and pick the tail strategy from what the launch sees:
+                                       //    q_ctrl[5] = 1 (time slices) once >= 5 % of the completed trajectories ran into the
+                                       //    pass budget, = 2 (hand-off) if the work runs out first
   long long q_handoff;                 // > 0 (run-to-completion only): once all trajectories have been started and at most
                                        // this many are still live, they are left in the ring for the warp-per-trajectory
                                        // kernel, which advances a lone trajectory ~5x faster (rollout_warp.cuh, RESUME)
@@ -154,14 +159,16 @@ __global__ void __launch_bounds__(128, (D == 1 ? 8 : (D <= 4 ? 5 : 4))) rollout_
   const bool want_l2 = (D == 1) && A.policy_opt != nullptr && A.l2 != nullptr;
   const long long lim = inject ? (A.noise_steps < A.n_steps_lim ? A.noise_steps : A.n_steps_lim) : A.n_steps_lim;
   typedef ContRec<D, F64> Rec;
-  const bool sliced = A.q_ring != nullptr && A.q_quantum > 0;
-  const bool handoff = A.q_ring != nullptr && A.q_quantum == 0 && A.q_handoff > 0;
+  // tail strategy: 1 = time slices, 2 = hand-off to the latency kernel, 3 = none, 0 = adaptive launch, not decided yet
+  const bool adaptive = A.q_ring != nullptr && A.q_adaptive != 0;
+  const bool tracked = A.q_ring != nullptr && (A.q_quantum > 0 || A.q_handoff > 0);
+  int mode = adaptive ? 0 : (A.q_ring != nullptr && A.q_quantum > 0 ? 1 : (A.q_ring != nullptr && A.q_handoff > 0 ? 2 : 3));
   Rec* const ring = reinterpret_cast<Rec*>(A.q_ring);
   // live state is kept small (the register budget of 8 blocks per SM is 64): while a lane waits for a record, `traj`
   // holds the record's index; slices end where the pass index is a multiple of the quantum (a power of two)
   const int qmask = A.q_quantum - 1;
 
-  bool alive = false, exhausted = false, pending = false, fin = false;
+  bool alive = false, exhausted = false, pending = false, fin = false, capped = false;
   long long traj = 0;
   int k = 0, ck = 0;
   real x[D];
@@ -174,7 +181,7 @@ __global__ void __launch_bounds__(128, (D == 1 ? 8 : (D <= 4 ? 5 : 4))) rollout_
 
   for (unsigned it = 0;; ++it) {
     if ((it & (SPB - 1)) == 0) {
-      if (sliced || handoff) {
+      if (tracked) {
         // (a) report the trajectories that completed since the last boundary
         const unsigned fm = __ballot_sync(FULL, fin);
         if (fm) {
@@ -182,7 +189,31 @@ __global__ void __launch_bounds__(128, (D == 1 ? 8 : (D <= 4 ? 5 : 4))) rollout_
           fin = false;
         }
       }
-      if (handoff && (it & (4u * SPB - 1u)) == 0) {
+      if (mode == 0) {
+        // adaptive launch, tail strategy not decided yet: count the trajectories that ran into the pass budget and, every
+        // other boundary, look whether somebody has decided / whether it is time to decide for time slices
+        const unsigned cm = __ballot_sync(FULL, capped);
+        if (cm) {
+          if (lane == __ffs(cm) - 1) atomicAdd(A.q_ctrl + 4, (unsigned long long)__popc(cm));
+          capped = false;
+        }
+        if ((it & (2u * SPB - 1u)) == 0) {
+          unsigned long long m = 0;
+          if (lane == 0) {
+            m = *reinterpret_cast<volatile unsigned long long*>(A.q_ctrl + 5);
+            if (m == 0) {
+              const unsigned long long n_cap = *reinterpret_cast<volatile unsigned long long*>(A.q_ctrl + 4);
+              const unsigned long long n_done = *reinterpret_cast<volatile unsigned long long*>(A.q_ctrl + 2);
+              if (n_done >= 4096 && n_cap * 20 >= n_done) {
+                const unsigned long long old = atomicCAS(A.q_ctrl + 5, 0ull, 1ull);
+                m = old == 0 ? 1 : old;
+              }
+            }
+          }
+          mode = (int)__shfl_sync(FULL, m, 0);
+        }
+      }
+      if (mode == 2 && (it & (4u * SPB - 1u)) == 0) {
         // every 4th boundary: is this the tail of the launch?  then leave the live trajectories to the latency kernel
         const unsigned long long claimed = *reinterpret_cast<volatile unsigned long long*>(A.q_ctrl);
         const unsigned long long completed = *reinterpret_cast<volatile unsigned long long*>(A.q_ctrl + 2);
@@ -203,7 +234,7 @@ __global__ void __launch_bounds__(128, (D == 1 ? 8 : (D <= 4 ? 5 : 4))) rollout_
           break;
         }
       }
-      if (sliced) {
+      if (mode == 1) {
         // (b) slice over: append the trajectory to the FIFO
         const bool expire = alive && k != 0 && (k & qmask) == 0;   // (a resumed lane is past this check: it resumes in (d))
         const unsigned em = __ballot_sync(FULL, expire);
@@ -244,15 +275,23 @@ __global__ void __launch_bounds__(128, (D == 1 ? 8 : (D <= 4 ? 5 : 4))) rollout_
             G = 0; S = 0; L2 = 0;
 #pragma unroll
             for (int i = 0; i < D; ++i) x[i] = F64 ? (real)A.x0_d[i] : (real)A.x0_f[i];
-          } else if (sliced) {
-            pending = true; traj = idx - A.K;
           } else {
-            exhausted = true;
+            // no fresh work left.  An undecided adaptive launch decides now: nothing ran into the budget, so the tail
+            // is a few long trajectories -> hand-off (unless another warp has just chosen time slices)
+            if (mode == 0) {
+              const unsigned long long old = atomicCAS(A.q_ctrl + 5, 0ull, 2ull);
+              mode = old == 0 ? 2 : (int)old;
+            }
+            if (mode == 1) { pending = true; traj = idx - A.K; }
+            else exhausted = true;
           }
         }
       }
+      // the tail strategy is a property of the launch (one global decision): lanes that have just learnt it in (c) tell
+      // the rest of the warp, so that `mode` stays warp-uniform (the blocks above use full-mask collectives)
+      if (adaptive) mode = (int)__reduce_max_sync(FULL, (unsigned)mode);
       // (d) lanes waiting for a record look at their slot; the other lanes of the warp are not held up
-      if (sliced && pending) {
+      if (pending) {
         Rec* r = ring + (traj & (A.q_cap - 1));
         const int epoch = (int)(traj >> A.q_cap_log2) + 1;
         volatile int* seq = &r->seq;
@@ -444,7 +483,7 @@ __global__ void __launch_bounds__(128, (D == 1 ? 8 : (D <= 4 ? 5 : 4))) rollout_
             if (A.logw) ((float*)A.logw)[traj] = (float)G - (float)S;
           }
           A.T[traj] = -1;
-          alive = false; fin = true;
+          alive = false; fin = true; capped = true;
         }
       }
     }

@@ -168,7 +168,9 @@ __global__ void __launch_bounds__(128, (D <= 2 ? 4 : 1)) rollout_fwd_warp_kernel
   P.load(W, lane);
 
   typedef ContRec<D, F64> Rec;
-  const long long n_items = RESUME ? (long long)A.q_ctrl[1] : A.K;
+  // RESUME: the records K1 appended when it handed its tail over; none if its launch went for time slices instead
+  // (q_ctrl[5] == 1: the ring then holds the FIFO's consumed records)
+  const long long n_items = RESUME ? (A.q_ctrl[5] == 1 ? 0 : (long long)A.q_ctrl[1]) : A.K;
   // fresh batches: static round robin (deterministic reverse-pass partials rely on nothing here, but it is free);
   // resumed tails: lengths differ by orders of magnitude, so warps take records from a counter as they become free
   auto next_item = [&](long long prev) -> long long {

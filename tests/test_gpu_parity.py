@@ -800,3 +800,29 @@ def test_step_vectorized_stopped_intended_semantics(golden, d):
     assert np.array_equal(done, nxt >= 1.0) and np.array_equal(db, dbt.astype(np.float32))
     empty = env.step_vectorized_stopped(states, actions, np.array([], dtype=int))
     assert np.array_equal(empty[0], states.astype(np.float64)) and empty[3].shape == (0, d)
+
+
+@pytest.mark.parametrize("lim,bias", [(600, 0.3), (20000, 1.0)])
+def test_adaptive_tail_strategy_is_bit_identical(monkeypatch, lim, bias):
+    """Default launches start running to completion and pick the tail strategy from what they see (time slices once 5 %
+    of the completed trajectories have run into the budget, otherwise the hand-off).  Whatever they pick, per-trajectory
+    results equal those of the forced schedules bit for bit: one workload with ~25 % capped trajectories, one with none."""
+    from rl_sde_is_b200 import _lib as L, rollout as R
+    from rl_sde_is_b200.models import DeterministicPolicy
+    env = _make_env(1, 1.0, 1.0, 0.005)
+    torch.manual_seed(11)
+    model = DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    model.policy[4].bias.data.fill_(bias)
+    params = R.flat_parameters(model).detach().numpy()
+    env_c, mlp_c = R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(1, 32)
+    K = 80000
+    monkeypatch.delenv("RLSDE_FWD_QUANTUM", raising=False)
+    monkeypatch.delenv("RLSDE_FWD_HANDOFF", raising=False)
+    auto = R.rollout_forward(env_c, mlp_c, params, K, seed=31, n_steps_lim=lim, stoch_int="exact", want_logw=True)
+    frac_capped = float((auto.T < 0).float().mean())
+    assert (frac_capped > 0.1) if lim == 600 else (frac_capped == 0.0)
+    for q in ("0", "8"):
+        monkeypatch.setenv("RLSDE_FWD_QUANTUM", q)
+        forced = R.rollout_forward(env_c, mlp_c, params, K, seed=31, n_steps_lim=lim, stoch_int="exact", want_logw=True)
+        assert torch.equal(auto.G, forced.G) and torch.equal(auto.S, forced.S) and torch.equal(auto.T, forced.T)
+        assert torch.equal(auto.logw, forced.logw) and np.array_equal(auto.stats, forced.stats)
