@@ -234,7 +234,7 @@ int rlsde_reduce_stats(int64_t K, int64_t n_steps_lim, uint32_t flags, const voi
  * folded into rows 0 and Ns-1; for s in the target set: 1/|TS| if s' in TS else 0.
  * h_half is the bin half-width (the reference passes h_state / 2, dynamic_programming.py:34).
  * state_grid_uniform != 0: the caller asserts that the state grid is equally spaced (to ~1e-14); cells no wider than
- * 0.25 sd are then integrated by Gauss-Legendre quadrature with a density recurrence along s' (|error| < 1e-13)
+ * 0.2 sd are then integrated by Gauss-Legendre quadrature with a density recurrence along s' (|error| < 1e-13)
  * instead of two erf/erfc evaluations per cell.  0 always takes the erf/erfc path.
  */
 int rlsde_tables(const double* state_grid_dev, int64_t Ns, const double* action_grid_dev, int64_t Na,

@@ -826,3 +826,24 @@ def test_adaptive_tail_strategy_is_bit_identical(monkeypatch, lim, bias):
         forced = R.rollout_forward(env_c, mlp_c, params, K, seed=31, n_steps_lim=lim, stoch_int="exact", want_logw=True)
         assert torch.equal(auto.G, forced.G) and torch.equal(auto.S, forced.S) and torch.equal(auto.T, forced.T)
         assert torch.equal(auto.logw, forced.logw) and np.array_equal(auto.stats, forced.stats)
+
+
+@pytest.mark.parametrize("alpha,beta,dt,h", [(1.0, 4.0, 0.001, 0.004), (5.0, 1.0, 0.005, 0.016), (1.0, 1.0, 0.001, 0.008)])
+def test_table_quadrature_path_against_exact_cdf_path(alpha, beta, dt, h):
+    """The Gauss-Legendre / recurrence path of the table builder at cell widths between 0.1 and 0.2 sd, against the
+    erf/erfc path (the reference's formula literally) on the same device: |dP| < 1e-13, columns sum to 1."""
+    from rl_sde_is_b200.dynamic_programming import compute_p_tensor_batch, p_tensor_column_sums
+    from rl_sde_is_b200.environments import DoubleWellStoppingTime1D
+    env = DoubleWellStoppingTime1D(beta=beta, alpha=alpha, dt=dt)
+    env.set_action_space_bounds()
+    env.discretize_state_space(h)
+    env.discretize_action_space(0.25)
+    d_cell = h / (env.sigma * np.sqrt(dt))
+    assert 0.1 < d_cell <= 0.2
+    fast = compute_p_tensor_batch(env, device_out=True)
+    exact = compute_p_tensor_batch(env, device_out=True, exact_cdf=True)
+    assert float((fast - exact).abs().max()) < 1e-13
+    assert np.abs(p_tensor_column_sums(fast).cpu().numpy() - 1).max() < 1e-12
+    # slabs of the fast path are exactly the rows of the full tensor
+    slab = compute_p_tensor_batch(env, device_out=True, sprime_range=(37, 211))
+    assert torch.equal(slab, fast[37:211])
