@@ -129,6 +129,11 @@ __device__ __forceinline__ void em_step_f32(const FwdArgs& A, float (&x)[D], con
 //   d = 1:  2 blocks (210 registers) 63.3 ms, 3 blocks (168) 61.4 ms, 4 blocks (128, 16 B of spills) 58.2 ms
 //   d = 10: 2 blocks 22.4 ms, 3 blocks 27.4 ms, 4 blocks 29.8 ms (the wider head spills)
 //   d = 2 (K = 2e5): 2 blocks + swizzled tiles 8.0 ms, 3 blocks + padded tiles 7.0 ms; d = 10: 20.3 vs 20.9 ms
+// unroll factor of the three 32-row inner products of a warp-pass (B200, d = 1 K = 4e5: 2 -> 36.6 ms, 4 -> 35.3, 8 -> 35.2, 32 -> 48.7; d = 10: 48.9 / 47.8 / 49.7)
+#ifndef RLSDE_BWD_UNROLL
+#define RLSDE_BWD_UNROLL 4
+#endif
+constexpr int kBwdUnroll = RLSDE_BWD_UNROLL;
 #ifndef RLSDE_BWD_MIN_BLOCKS
 #define RLSDE_BWD_MIN_BLOCKS(D) ((D) == 1 ? 4 : ((D) <= 4 ? 3 : 2))
 #endif
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MIN_BLOCKS(D)) rollout_bwd_kern
           for (int c = 0; c < CPL; ++c)
 #pragma unroll
             for (int i = 0; i < D; ++i) pW3[c][i] = 0.f;
-#pragma unroll 2
+#pragma unroll(kBwdUnroll)
           for (int r = 0; r < 32; ++r) {
             float ar[D];
 #pragma unroll
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MIN_BLOCKS(D)) rollout_bwd_kern
       float pb2[CPL];
 #pragma unroll
       for (int c = 0; c < CPL; ++c) pb2[c] = 0.f;
-#pragma unroll 2
+#pragma unroll(kBwdUnroll)
       for (int r = 0; r < 32; ++r) {
         float hv[CPL];
 #pragma unroll
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MIN_BLOCKS(D)) rollout_bwd_kern
 #pragma unroll
           for (int i = 0; i < D; ++i) pW1[c][i] = 0.f;
         }
-#pragma unroll 2
+#pragma unroll(kBwdUnroll)
         for (int r = 0; r < 32; ++r) {
           float xr[D];
 #pragma unroll
