@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define RLSDE_VERSION 100       /* 0.1.0 */
+#define RLSDE_VERSION 200       /* 0.2.0: rlsde_rollout_cfg grew the scheduling knobs */
 #define RLSDE_MAX_D 16          /* largest state / action dimension */
 #define RLSDE_NSTATS 16         /* doubles in a statistics record */
 
@@ -111,6 +111,17 @@ typedef struct rlsde_rollout_cfg {
      d == 1 only: idx = floor((clip(x, grid_lo, grid_hi) - grid_lo) / grid_h)  (environments.py:318-321) */
   int64_t n_grid;
   double grid_lo, grid_hi, grid_h;
+  /* scheduling knobs (tuning / tests only; 0 = automatic everywhere, so a zero-initialised struct is the default).
+     They change the schedule, never a per-trajectory result (tested bit for bit).  The library itself reads no
+     environment variables; the Python binding maps RLSDE_FWD_QUANTUM / RLSDE_FWD_HANDOFF / RLSDE_BWD_WARP_SHARE /
+     RLSDE_FWD_BLOCKS_PER_SM onto these fields. */
+  int32_t fwd_quantum;          /* thread-per-trajectory forward kernel: n > 0 = time slices of n passes, -1 = run to
+                                   completion (+ tail hand-off), 0 = adaptive */
+  int32_t fwd_blocks_per_sm;    /* n > 0: cap on resident blocks per SM of the forward kernel */
+  int64_t fwd_handoff;          /* live trajectories at which the tail goes to the warp-per-trajectory kernel
+                                   (-1 = never, 0 = automatic) */
+  int64_t bwd_warp_share;       /* longest trajectories the reverse pass gives to the warp-per-trajectory kernel
+                                   (-1 = none, 0 = automatic) */
 } rlsde_rollout_cfg;
 
 /* layout of a statistics record (double[RLSDE_NSTATS]); sums are over the K local trajectories,
@@ -213,12 +224,30 @@ int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
  *   G/S/T/stats/grad: this iteration's per-trajectory results, statistics record and gradient of
  *   mean_k(-G_k - sg(G_k) S_k) -- e.g. rows of a device-side log the caller reads once at the end.
  * A trajectory that does not reach the target set within n_steps_lim contributes nothing to the gradient and is
- * counted in stats[RLSDE_ST_N_UNFINISHED]; the caller decides what to do about it when it reads the log.
+ * counted in stats[RLSDE_ST_N_UNFINISHED]; such a batch does NOT update theta / m / v (the Adam kernel looks at the
+ * count on the device), and the caller sees it when it reads the log.
  */
 int rlsde_reinforce_step(const rlsde_env* env, const rlsde_mlp* mlp, float* theta_dev, float* adam_m_dev, float* adam_v_dev,
                          const rlsde_rollout_cfg* cfg, const float* noise_dev, double lr, double beta1, double beta2,
                          double eps, int64_t step_t, float* G_dev, float* S_dev, int32_t* T_dev, float* path_dev,
                          double* stats_dev, float* grad_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/*
+ * The same iteration split in two for data-parallel training (trajectories sharded over the GPUs of a box,
+ * ONE exchange per iteration).  rlsde_reinforce_rollout runs this rank's shard (cfg.K of cfg.K_global trajectories,
+ * gradient scaled by 1 / K_global) and leaves the row  [grad as P doubles | statistics record]  in packed_dev
+ * (double[P + RLSDE_NSTATS]).  The caller all-gathers the rows of all ranks (one collective, e.g. ncclAllGather through
+ * torch.distributed, enqueued on the same stream) and hands the n_ranks rows to rlsde_reinforce_apply, which adds them
+ * in rank order -- every rank forms bit-identical sums -- writes the global gradient / statistics (optional outputs)
+ * and takes the Adam step, unless some rank reported an unfinished trajectory.
+ */
+int rlsde_reinforce_rollout(const rlsde_env* env, const rlsde_mlp* mlp, const float* theta_dev, const rlsde_rollout_cfg* cfg,
+                            const float* noise_dev, float* G_dev, float* S_dev, int32_t* T_dev, float* path_dev,
+                            double* stats_dev, float* grad_dev, double* packed_dev, void* workspace_dev,
+                            size_t workspace_bytes, void* stream);
+int rlsde_reinforce_apply(const rlsde_mlp* mlp, float* theta_dev, float* adam_m_dev, float* adam_v_dev,
+                          const double* packed_all_dev, int32_t n_ranks, double lr, double beta1, double beta2, double eps,
+                          int64_t step_t, float* grad_out_dev, double* stats_out_dev, void* stream);
 
 /* Deterministic fp64 reduction of per-trajectory outputs into a statistics record. */
 int rlsde_reduce_stats(int64_t K, int64_t n_steps_lim, uint32_t flags, const void* G_dev, const void* S_dev,

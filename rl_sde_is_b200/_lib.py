@@ -38,6 +38,7 @@ EXPORTED_SYMBOLS = [
     "rlsde_param_count", "rlsde_workspace_bytes", "rlsde_rollout_fwd", "rlsde_rollout_bwd", "rlsde_reduce_stats",
     "rlsde_tables", "rlsde_tables_colsum", "rlsde_env_step", "rlsde_noise_fill",
     "rlsde_dp_scratch_bytes", "rlsde_dp_sweep", "rlsde_dp_rowmax", "rlsde_rollout_transitions", "rlsde_launch_count", "rlsde_reinforce_step",
+    "rlsde_reinforce_rollout", "rlsde_reinforce_apply",
 ]
 
 
@@ -60,6 +61,8 @@ class RlsdeRolloutCfg(C.Structure):
         ("n_steps_lim", C.c_int64), ("noise_steps", C.c_int64), ("flags", C.c_uint32), ("ckpt_every", C.c_int32),
         ("ckpt_stride", C.c_int64), ("n_grid", C.c_int64),
         ("grid_lo", C.c_double), ("grid_hi", C.c_double), ("grid_h", C.c_double),
+        # scheduling knobs, 0 = automatic (include/rlsde.h)
+        ("fwd_quantum", C.c_int32), ("fwd_blocks_per_sm", C.c_int32), ("fwd_handoff", C.c_int64), ("bwd_warp_share", C.c_int64),
     ]
 
 
@@ -98,6 +101,9 @@ def load():
                                               vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.rlsde_reinforce_step.argtypes = [C.POINTER(RlsdeEnv), C.POINTER(RlsdeMlp), vp, vp, vp, C.POINTER(RlsdeRolloutCfg), vp,
                                          dbl, dbl, dbl, dbl, i64, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.rlsde_reinforce_rollout.argtypes = [C.POINTER(RlsdeEnv), C.POINTER(RlsdeMlp), vp, C.POINTER(RlsdeRolloutCfg), vp,
+                                            vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.rlsde_reinforce_apply.argtypes = [C.POINTER(RlsdeMlp), vp, vp, vp, vp, i32, dbl, dbl, dbl, dbl, i64, vp, vp, vp]
     lib.rlsde_rollout_bwd.argtypes = [C.POINTER(RlsdeEnv), C.POINTER(RlsdeMlp), vp, C.POINTER(RlsdeRolloutCfg),
                                       vp, vp, vp, vp, vp, dbl, vp, vp, C.c_size_t, vp]
     lib.rlsde_reduce_stats.argtypes = [i64, i64, u32, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
@@ -111,10 +117,35 @@ def load():
     lib.rlsde_dp_rowmax.argtypes = [vp, i64, i64, vp, vp, vp]
     for name in ("rlsde_device_info", "rlsde_supported", "rlsde_rollout_fwd", "rlsde_rollout_bwd", "rlsde_reduce_stats",
                  "rlsde_tables", "rlsde_tables_colsum", "rlsde_env_step", "rlsde_noise_fill", "rlsde_dp_sweep", "rlsde_dp_rowmax",
-                 "rlsde_rollout_transitions", "rlsde_reinforce_step"):
+                 "rlsde_rollout_transitions", "rlsde_reinforce_step", "rlsde_reinforce_rollout", "rlsde_reinforce_apply"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib
+
+
+def apply_tuning(cfg, tuning=None):
+    """Scheduling knobs of a rollout cfg (include/rlsde.h: they change the schedule, never a result).  ``tuning`` is a dict
+    with any of ``fwd_quantum`` (passes per time slice, 0 = run to completion), ``fwd_handoff``, ``bwd_warp_share``,
+    ``fwd_blocks_per_sm``; keys that are absent fall back to the environment variables RLSDE_FWD_QUANTUM,
+    RLSDE_FWD_HANDOFF, RLSDE_BWD_WARP_SHARE, RLSDE_FWD_BLOCKS_PER_SM (read HERE, in Python -- the library reads none),
+    and to "automatic" if those are unset too."""
+    tuning = tuning or {}
+
+    def knob(name):
+        if name in tuning and tuning[name] is not None:
+            return int(tuning[name])
+        v = os.environ.get("RLSDE_" + name.upper())
+        return int(v) if v not in (None, "") else None
+
+    q = knob("fwd_quantum")
+    cfg.fwd_quantum = 0 if q is None else (q if q > 0 else -1)
+    h = knob("fwd_handoff")
+    cfg.fwd_handoff = 0 if h is None else (h if h > 0 else -1)
+    w = knob("bwd_warp_share")
+    cfg.bwd_warp_share = 0 if w is None else (w if w > 0 else -1)
+    b = knob("fwd_blocks_per_sm")
+    cfg.fwd_blocks_per_sm = 0 if b is None or b < 1 else b
+    return cfg
 
 
 def check(status, what):

@@ -8,12 +8,43 @@ namespace rlsde {
 // torch.optim.Adam's update for one flat parameter vector (amsgrad / weight decay / maximize off), the step the
 // reference takes after eff_loss.backward() (reinforce_deterministic_core.py:143-146,243):
 //   m <- m + (g - m)(1 - beta1);  v <- v beta2 + (1 - beta2) g g;  theta <- theta - (lr / bc1) m / (sqrt(v) / sqrt(bc2) + eps)
-__global__ void adam_step_kernel(int P, float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
+// The gradient comes either from this GPU alone (n_ranks == 0: grad float[P], stats double[NSTATS]) or as the rows
+// `[grad (P doubles) | stats (NSTATS doubles)]` that the ranks of a data-parallel job exchanged with ONE all-gather
+// (n_ranks >= 1: packed double[n_ranks][P + NSTATS]); rows are added in rank order, so every rank forms the same bits.
+// A batch in which any trajectory ran into the pass budget (stats[N_UNFINISHED] > 0) is dropped from the gradient by
+// the reverse pass; applying the remainder scaled by 1/K would be a biased step, so the update is skipped on the
+// device (theta, m, v untouched) and the caller sees the count in the statistics record.
+__global__ void adam_step_kernel(int P, int n_ranks, const float* __restrict__ grad, const double* __restrict__ stats,
+                                 const double* __restrict__ packed, float* __restrict__ theta, float* __restrict__ m,
                                  float* __restrict__ v, float one_minus_b1, float b2, float one_minus_b2, float eps,
-                                 float step_size, float bc2_sqrt) {
+                                 float step_size, float bc2_sqrt, float* __restrict__ grad_out, double* __restrict__ stats_out) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = P + RLSDE_NSTATS;
+  double unfinished = 0.0;
+  if (n_ranks > 0) {
+    for (int r = 0; r < n_ranks; ++r) unfinished += packed[(long long)r * row + P + RLSDE_ST_N_UNFINISHED];
+  } else {
+    unfinished = stats[RLSDE_ST_N_UNFINISHED];
+  }
+  if (n_ranks > 0 && p < RLSDE_NSTATS && stats_out != nullptr) {
+    double acc = packed[P + p];
+    for (int r = 1; r < n_ranks; ++r) {
+      const double x = packed[(long long)r * row + P + p];
+      acc = (p == RLSDE_ST_MAX_T) ? (x > acc ? x : acc) : acc + x;
+    }
+    stats_out[p] = acc;
+  }
   if (p >= P) return;
-  const float g = grad[p];
+  float g;
+  if (n_ranks > 0) {
+    double acc = 0.0;
+    for (int r = 0; r < n_ranks; ++r) acc += packed[(long long)r * row + p];
+    g = (float)acc;
+    if (grad_out != nullptr) grad_out[p] = g;
+  } else {
+    g = grad[p];
+  }
+  if (unfinished > 0.0) return;
   const float mp = __fmaf_rn(__fsub_rn(g, m[p]), one_minus_b1, m[p]);
   const float vp = __fadd_rn(__fmul_rn(v[p], b2), __fmul_rn(__fmul_rn(one_minus_b2, g), g));
   m[p] = mp;
@@ -22,11 +53,28 @@ __global__ void adam_step_kernel(int P, float* __restrict__ theta, const float* 
   theta[p] = __fsub_rn(theta[p], __fmul_rn(step_size, __fdiv_rn(mp, denom)));
 }
 
-int launch_adam_step(int P, float* theta, const float* grad, float* m, float* v, double lr, double beta1, double beta2,
-                     double eps, long long step_t, cudaStream_t stream) {
+int launch_adam_step(int P, int n_ranks, const float* grad, const double* stats, const double* packed, float* theta, float* m,
+                     float* v, double lr, double beta1, double beta2, double eps, long long step_t, float* grad_out,
+                     double* stats_out, cudaStream_t stream) {
   const double bc1 = 1.0 - pow(beta1, (double)step_t), bc2 = 1.0 - pow(beta2, (double)step_t);
-  adam_step_kernel<<<(P + 127) / 128, 128, 0, stream>>>(P, theta, grad, m, v, (float)(1.0 - beta1), (float)beta2,
-                                                        (float)(1.0 - beta2), (float)eps, (float)(lr / bc1), (float)sqrt(bc2));
+  const int n = P > RLSDE_NSTATS ? P : RLSDE_NSTATS;
+  adam_step_kernel<<<(n + 127) / 128, 128, 0, stream>>>(P, n_ranks, grad, stats, packed, theta, m, v, (float)(1.0 - beta1),
+                                                        (float)beta2, (float)(1.0 - beta2), (float)eps, (float)(lr / bc1),
+                                                        (float)sqrt(bc2), grad_out, stats_out);
+  note_kernel_launches(1);
+  return (int)cudaGetLastError();
+}
+
+// packed[0 .. P) = grad (as doubles), packed[P .. P + NSTATS) = stats: this rank's row of the iteration's one exchange
+__global__ void pack_grad_stats_kernel(int P, const float* __restrict__ grad, const double* __restrict__ stats,
+                                       double* __restrict__ packed) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) packed[p] = (double)grad[p];
+  else if (p < P + RLSDE_NSTATS) packed[p] = stats[p - P];
+}
+
+int launch_pack_grad_stats(int P, const float* grad, const double* stats, double* packed, cudaStream_t stream) {
+  pack_grad_stats_kernel<<<(P + RLSDE_NSTATS + 127) / 128, 128, 0, stream>>>(P, grad, stats, packed);
   note_kernel_launches(1);
   return (int)cudaGetLastError();
 }

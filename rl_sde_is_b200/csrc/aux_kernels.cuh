@@ -27,8 +27,10 @@ struct StepArgs {
 
 int launch_reduce_stats(long long K, long long n_steps_lim, bool f64, const void* G, const void* S, const int* T,
                         const void* l2, const void* logw, double* stats, double* partial, cudaStream_t stream);
-int launch_adam_step(int P, float* theta, const float* grad, float* m, float* v, double lr, double beta1, double beta2,
-                     double eps, long long step_t, cudaStream_t stream);
+int launch_adam_step(int P, int n_ranks, const float* grad, const double* stats, const double* packed, float* theta, float* m,
+                     float* v, double lr, double beta1, double beta2, double eps, long long step_t, float* grad_out,
+                     double* stats_out, cudaStream_t stream);
+int launch_pack_grad_stats(int P, const float* grad, const double* stats, double* packed, cudaStream_t stream);
 int launch_noise_fill(unsigned long long seed, long long traj_offset, long long K, int d, long long pass_begin,
                       long long n_pass, double dt, float* out, cudaStream_t stream);
 int launch_env_step(const StepArgs& A, bool f64, cudaStream_t stream);

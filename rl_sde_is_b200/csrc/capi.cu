@@ -1,7 +1,7 @@
 // C ABI of librlsde_b200.so (declared in include/rlsde.h): argument checking, host-side
 // precomputation of the environment constants the way torch / numpy round them, dispatch on the
-// policy shape, and stream-ordered launches.  No torch types, no exceptions, no global mutable state
-// except the thread-local text of the last CUDA error.
+// policy shape, and stream-ordered launches.  No torch types, no exceptions, no environment variables, no
+// global mutable state except the thread-local text of the last CUDA error and the launch counter.
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -83,16 +83,26 @@ static void fill_env(const rlsde_env* env, FwdArgs& A) {
 
 static int fill_cfg(const rlsde_rollout_cfg* cfg, FwdArgs& A) {
   if (!cfg || cfg->K < 0 || cfg->n_steps_lim < 1 || cfg->n_steps_lim > 2000000000LL) return RLSDE_ERR_INVALID_ARG;
+  if (cfg->traj_offset < 0) return RLSDE_ERR_INVALID_ARG;
   if ((cfg->flags & RLSDE_F_NOISE_INJECTED) && cfg->noise_steps < 1) return RLSDE_ERR_INVALID_ARG;
-  if ((cfg->flags & RLSDE_F_STORE_PATH) && (cfg->ckpt_every < 1 || cfg->ckpt_stride < 1)) return RLSDE_ERR_INVALID_ARG;
+  // injected noise is indexed [pass][traj_offset + k] with row stride K_global: the shard must lie inside the global batch
+  if ((cfg->flags & RLSDE_F_NOISE_INJECTED) && cfg->traj_offset + cfg->K > (cfg->K_global > 0 ? cfg->K_global : cfg->K))
+    return RLSDE_ERR_INVALID_ARG;
   A.K = cfg->K; A.traj_offset = cfg->traj_offset;
   A.K_global = cfg->K_global > 0 ? cfg->K_global : cfg->K;
   A.seed = cfg->seed; A.n_steps_lim = cfg->n_steps_lim; A.noise_steps = cfg->noise_steps;
   A.flags = cfg->flags; A.ckpt_every = cfg->ckpt_every > 0 ? cfg->ckpt_every : 1; A.ckpt_stride = cfg->ckpt_stride;
+  if (cfg->flags & RLSDE_F_STORE_PATH) {
+    // the kernels write path[(traj * ckpt_stride + k / ckpt_every) * d] for every pass k they execute
+    const long long lim_eff = (cfg->flags & RLSDE_F_NOISE_INJECTED) && cfg->noise_steps < cfg->n_steps_lim ? cfg->noise_steps
+                                                                                                             : cfg->n_steps_lim;
+    if (cfg->ckpt_every < 1 || cfg->ckpt_stride < (lim_eff + cfg->ckpt_every - 1) / cfg->ckpt_every) return RLSDE_ERR_INVALID_ARG;
+  }
   A.ckpt_log2 = -1;
   for (int b = 0; b < 31; ++b)
     if (A.ckpt_every == (1 << b)) A.ckpt_log2 = b;
   A.n_grid = cfg->n_grid; A.grid_lo = cfg->grid_lo; A.grid_hi = cfg->grid_hi; A.grid_h = cfg->grid_h;
+  A.blocks_per_sm_cap = cfg->fwd_blocks_per_sm > 0 ? cfg->fwd_blocks_per_sm : 0;
   return RLSDE_OK;
 }
 
@@ -224,7 +234,7 @@ static int rollout_fwd_impl(const rlsde_env* env, const rlsde_mlp* mlp, const fl
     const bool can_hand_off = mlp->d_hidden == WARP_H && !tr.base;     // the latency kernel has no transition stream
     A.q_adaptive = can_hand_off ? 1 : 0;
     if (!can_hand_off && lim_eff > 4096) quantum = 0;
-    if (const char* ev = getenv("RLSDE_FWD_QUANTUM")) { quantum = atoll(ev); A.q_adaptive = 0; }
+    if (cfg->fwd_quantum != 0) { quantum = cfg->fwd_quantum > 0 ? cfg->fwd_quantum : 0; A.q_adaptive = 0; }
     if (quantum > 0) {                                    // a power of two, at least one noise block (4 passes)
       long long q2 = 4;
       while (q2 < quantum && q2 < (1LL << 30)) q2 <<= 1;
@@ -232,8 +242,8 @@ static int rollout_fwd_impl(const rlsde_env* env, const rlsde_mlp* mlp, const fl
     }
     A.q_quantum = (int)quantum;
     A.q_handoff = (can_hand_off && (quantum == 0 || A.q_adaptive)) ? 4LL * warp_path_max_k(sm) : 0;
-    if (const char* ev = getenv("RLSDE_FWD_HANDOFF")) {
-      if (A.q_handoff > 0) A.q_handoff = atoll(ev);
+    if (cfg->fwd_handoff != 0) {
+      if (A.q_handoff > 0) A.q_handoff = cfg->fwd_handoff;
       if (A.q_handoff <= 0) { A.q_handoff = 0; A.q_adaptive = 0; }
     }
   }
@@ -300,6 +310,7 @@ int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
   if ((rc = fill_cfg(cfg, A)) != RLSDE_OK) return rc;
   if (A.flags & RLSDE_F_STATE_F64) return RLSDE_ERR_UNSUPPORTED;   // the reference differentiates the f32 torch path only
   if (!(A.flags & RLSDE_F_STORE_PATH)) return RLSDE_ERR_INVALID_ARG;
+  if (A.ckpt_every > BWD_MAX_SEG) return RLSDE_ERR_INVALID_ARG;        // the reverse pass recomputes at most 32 passes per checkpoint
   if ((A.flags & RLSDE_F_NOISE_INJECTED) && !noise_dev) return RLSDE_ERR_INVALID_ARG;
   A.noise = noise_dev;
   A.G = (void*)G_dev; A.T = (int*)T_dev; A.path = (float*)path_dev;
@@ -321,7 +332,7 @@ int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
   if (!warp_path && order_dev && A.ckpt_every == 1 && mlp->d_hidden == WARP_H && A.K > (long long)sm * 128) {
     // measured (K = 4e5, d = 1): 46.2 / 36.7 / 36.7 / 37.5 / 41.9 ms at 0 / 2 368 / 4 736 / 9 472 / 25 000 long trajectories
     n_long = A.K / 16 < warp_path_max_k(sm) ? A.K / 16 : warp_path_max_k(sm);
-    if (const char* ev = getenv("RLSDE_BWD_WARP_SHARE")) n_long = atoll(ev) < A.K ? atoll(ev) : A.K;
+    if (cfg->bwd_warp_share != 0) n_long = cfg->bwd_warp_share < A.K ? cfg->bwd_warp_share : A.K;
     if (n_long < 0) n_long = 0;
   }
   FwdArgs Abulk = A;
@@ -349,16 +360,14 @@ int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
   return RLSDE_OK;
 }
 
-int rlsde_reinforce_step(const rlsde_env* env, const rlsde_mlp* mlp, float* theta_dev, float* adam_m_dev, float* adam_v_dev,
-                         const rlsde_rollout_cfg* cfg, const float* noise_dev, double lr, double beta1, double beta2,
-                         double eps, int64_t step_t, float* G_dev, float* S_dev, int32_t* T_dev, float* path_dev,
-                         double* stats_dev, float* grad_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+// rollout + statistics + reverse pass of one device-resident REINFORCE iteration (everything but the parameter update)
+static int reinforce_rollout_impl(const rlsde_env* env, const rlsde_mlp* mlp, const float* theta_dev, const rlsde_rollout_cfg* cfg,
+                                  const float* noise_dev, float* G_dev, float* S_dev, int32_t* T_dev, float* path_dev,
+                                  double* stats_dev, float* grad_dev, void* workspace_dev, size_t workspace_bytes,
+                                  cudaStream_t stream) {
   int rc = check_env_mlp(env, mlp);
   if (rc != RLSDE_OK) return rc;
-  if (!theta_dev || !adam_m_dev || !adam_v_dev || !G_dev || !S_dev || !T_dev || !path_dev || !stats_dev || !grad_dev ||
-      !workspace_dev || step_t < 1)
-    return RLSDE_ERR_INVALID_ARG;
+  if (!theta_dev || !G_dev || !S_dev || !T_dev || !path_dev || !stats_dev || !grad_dev || !workspace_dev) return RLSDE_ERR_INVALID_ARG;
   if (workspace_bytes < ws_fixed_bytes()) return RLSDE_ERR_WORKSPACE;
   static_assert(sizeof(MlpConst<RLSDE_MAX_D, WARP_H>) <= WS_POLICY_BYTES, "raise WS_POLICY_BYTES");
   FwdArgs A;
@@ -380,8 +389,8 @@ int rlsde_reinforce_step(const rlsde_env* env, const rlsde_mlp* mlp, float* thet
   double* stats_partial = (double*)((char*)workspace_dev + WS_COUNTER_BYTES);
   float* partial = (float*)((char*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES + WS_POLICY_BYTES);
   const bool fast = (A.flags & RLSDE_F_TANH_FAST) != 0;
-  const int P = (int)rlsde_param_count(mlp);
   const long long lim_eff = (A.flags & RLSDE_F_NOISE_INJECTED) && A.noise_steps < A.n_steps_lim ? A.noise_steps : A.n_steps_lim;
+  const float scale = (float)(1.0 / (double)A.K_global);       // the loss is the mean over ALL shards' trajectories
   int lrc = -1;
 #define X(D_, H_)                                                                                                        \
   if (env->d == D_ && mlp->d_hidden == H_ && H_ == WARP_H) {                                                             \
@@ -389,12 +398,52 @@ int rlsde_reinforce_step(const rlsde_env* env, const rlsde_mlp* mlp, float* thet
     if (lrc == 0) lrc = launch_rollout_fwd_warp<D_>(nullptr, W_dev, A, sm, stream);                                      \
     if (lrc == 0) lrc = launch_reduce_stats(A.K, lim_eff, false, G_dev, S_dev, T_dev, nullptr, nullptr, stats_dev,       \
                                             stats_partial, stream);                                                     \
-    if (lrc == 0) lrc = launch_rollout_bwd_warp<D_>(nullptr, W_dev, A, (float)(1.0 / (double)A.K), grad_dev, partial, sm, stream); \
+    if (lrc == 0) lrc = launch_rollout_bwd_warp<D_>(nullptr, W_dev, A, scale, grad_dev, partial, sm, stream);            \
   }
   RLSDE_SHAPES(X)
 #undef X
-  if (lrc != 0) return cuda_fail((cudaError_t)lrc, "reinforce_step launch");
-  lrc = launch_adam_step(P, theta_dev, grad_dev, adam_m_dev, adam_v_dev, lr, beta1, beta2, eps, step_t, stream);
+  if (lrc != 0) return cuda_fail((cudaError_t)lrc, "reinforce rollout launch");
+  return RLSDE_OK;
+}
+
+int rlsde_reinforce_step(const rlsde_env* env, const rlsde_mlp* mlp, float* theta_dev, float* adam_m_dev, float* adam_v_dev,
+                         const rlsde_rollout_cfg* cfg, const float* noise_dev, double lr, double beta1, double beta2,
+                         double eps, int64_t step_t, float* G_dev, float* S_dev, int32_t* T_dev, float* path_dev,
+                         double* stats_dev, float* grad_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!adam_m_dev || !adam_v_dev || step_t < 1) return RLSDE_ERR_INVALID_ARG;
+  const int rc = reinforce_rollout_impl(env, mlp, theta_dev, cfg, noise_dev, G_dev, S_dev, T_dev, path_dev, stats_dev, grad_dev,
+                                        workspace_dev, workspace_bytes, stream);
+  if (rc != RLSDE_OK) return rc;
+  const int P = (int)rlsde_param_count(mlp);
+  const int lrc = launch_adam_step(P, 0, grad_dev, stats_dev, nullptr, theta_dev, adam_m_dev, adam_v_dev, lr, beta1, beta2, eps,
+                                   step_t, nullptr, nullptr, stream);
+  if (lrc != 0) return cuda_fail((cudaError_t)lrc, "adam_step launch");
+  return RLSDE_OK;
+}
+
+int rlsde_reinforce_rollout(const rlsde_env* env, const rlsde_mlp* mlp, const float* theta_dev, const rlsde_rollout_cfg* cfg,
+                            const float* noise_dev, float* G_dev, float* S_dev, int32_t* T_dev, float* path_dev,
+                            double* stats_dev, float* grad_dev, double* packed_dev, void* workspace_dev, size_t workspace_bytes,
+                            void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!packed_dev) return RLSDE_ERR_INVALID_ARG;
+  const int rc = reinforce_rollout_impl(env, mlp, theta_dev, cfg, noise_dev, G_dev, S_dev, T_dev, path_dev, stats_dev, grad_dev,
+                                        workspace_dev, workspace_bytes, stream);
+  if (rc != RLSDE_OK) return rc;
+  const int lrc = launch_pack_grad_stats((int)rlsde_param_count(mlp), grad_dev, stats_dev, packed_dev, stream);
+  if (lrc != 0) return cuda_fail((cudaError_t)lrc, "pack_grad_stats launch");
+  return RLSDE_OK;
+}
+
+int rlsde_reinforce_apply(const rlsde_mlp* mlp, float* theta_dev, float* adam_m_dev, float* adam_v_dev,
+                          const double* packed_all_dev, int32_t n_ranks, double lr, double beta1, double beta2, double eps,
+                          int64_t step_t, float* grad_out_dev, double* stats_out_dev, void* stream_) {
+  if (!mlp || !theta_dev || !adam_m_dev || !adam_v_dev || !packed_all_dev || n_ranks < 1 || step_t < 1) return RLSDE_ERR_INVALID_ARG;
+  const int64_t P = rlsde_param_count(mlp);
+  if (P < 1) return RLSDE_ERR_INVALID_ARG;
+  const int lrc = launch_adam_step((int)P, n_ranks, nullptr, nullptr, packed_all_dev, theta_dev, adam_m_dev, adam_v_dev, lr, beta1,
+                                   beta2, eps, step_t, grad_out_dev, stats_out_dev, (cudaStream_t)stream_);
   if (lrc != 0) return cuda_fail((cudaError_t)lrc, "adam_step launch");
   return RLSDE_OK;
 }

@@ -72,6 +72,7 @@ struct FwdArgs {
   unsigned long long* counter;   // work counter of THIS launch (zeroed by the host wrapper)
   const long long* order;        // reverse pass: processing order of the trajectories (or nullptr = identity)
   int grad_accumulate;           // reverse pass: add this launch's gradient to grad instead of overwriting it
+  int blocks_per_sm_cap;         // > 0: cap on resident blocks per SM of the thread-per-trajectory forward kernel (tuning)
   // ---- transition stream (replay-buffer sampler, approximate_methods.py:513-545): trajectory `t` writes the tuple of
   //      its pass k at slot tr_base[t] + k of the five arrays below.  nullptr = no stream.
   const long long* tr_base;

@@ -1,6 +1,5 @@
 // Launcher + explicit instantiation helper for one policy shape (D, H) of the forward rollout.
 #pragma once
-#include <cstdlib>
 #include "rollout_fwd.cuh"
 
 namespace rlsde {
@@ -20,10 +19,7 @@ static int launch_fwd_variant(const float* params_host, const FwdArgs& args, int
   } else {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-    if (const char* e = getenv("RLSDE_FWD_BLOCKS_PER_SM")) {   // tuning knob (bench / profiling only)
-      const int v = atoi(e);
-      if (v >= 1 && v < per_sm) per_sm = v;
-    }
+    if (args.blocks_per_sm_cap >= 1 && args.blocks_per_sm_cap < per_sm) per_sm = args.blocks_per_sm_cap;   // tuning knob
     grid = (long long)sm_count * per_sm;
     const long long need = (args.K + block - 1) / block;
     if (grid > need) grid = need;

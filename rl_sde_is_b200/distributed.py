@@ -51,6 +51,16 @@ class Shard:
             stats[ST_MAX_T] = mx
         return stats
 
+    def all_gather_rows(self, row):
+        """``[world_size, n]`` tensor holding every rank's ``row`` (ONE collective).  All-gather rather than all-reduce:
+        the rows are then added in rank order by every rank itself, so all ranks form bit-identical sums whatever
+        algorithm NCCL picks, and the maximum entry of the statistics record survives the exchange."""
+        if self.world_size <= 1:
+            return row.reshape(1, -1)
+        out = torch.empty((self.world_size, row.numel()), dtype=row.dtype, device=row.device)
+        dist.all_gather_into_tensor(out, row.contiguous(), group=self.group)
+        return out
+
     @classmethod
     def from_env(cls, K_global, group=None):
         if dist.is_available() and dist.is_initialized():
@@ -65,6 +75,16 @@ def pack_grad_and_stats(grad, stats):
 
 def unpack_grad_and_stats(buf, n_params):
     return buf[:n_params].to(torch.float32), buf[n_params:]
+
+
+def reduce_gathered(rows, n_params):
+    """Rank-ordered sum of all-gathered ``[gradient | statistics]`` rows -> ``(grad float32[P], stats float64[NSTATS])``."""
+    from ._lib import ST_MAX_T
+    acc = rows[0].clone()
+    for r in range(1, rows.shape[0]):
+        acc = acc + rows[r]
+    acc[n_params + ST_MAX_T] = rows[:, n_params + ST_MAX_T].max()
+    return acc[:n_params].to(torch.float32), acc[n_params:]
 
 
 def merge_stats(records):

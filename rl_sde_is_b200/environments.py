@@ -43,7 +43,12 @@ class _DoubleWellBase:
         self.state_space_low, self.state_space_high = -2.0, 2.0
         self.action_space_low, self.action_space_high = 0.0, 3.0
         self.name = name_fmt.format(beta, alpha)
-        self.rng_seed = 0          # Philox key used by step()/step_torch() when no increments are passed
+        # Philox key of the increments step()/step_torch() draw when none are passed.  None = not chosen yet: the first
+        # such call takes it from the host generator the reference would have drawn from (np.random for step, torch for
+        # step_torch), so np.random.seed / torch.manual_seed make a run reproducible as they do for the reference, while
+        # two environments (train / test), two runs with different seeds or two processes do not replay the same noise.
+        # Assign an integer to pin it.
+        self.rng_seed = None
         self._pass_counter = 0
 
     # -- cheap closed forms, host side (used by tests, grids and plots, not by the kernels)
@@ -86,7 +91,21 @@ class _DoubleWellBase:
         return idx
 
     # -- one Euler-Maruyama pass on the GPU
-    def _device_step(self, state, action, f64, hit_rule, reward_type, dbt):
+    def _noise_key(self, source):
+        if self.rng_seed is None:
+            if source == "torch":
+                self.rng_seed = int(torch.randint(0, 2**62, (1,), dtype=torch.int64).item())
+            else:
+                self.rng_seed = int(np.random.randint(0, 2**62, dtype=np.int64))
+        return int(self.rng_seed)
+
+    @staticmethod
+    def _rank_offset():
+        """Ranks of a torch.distributed job must not share Brownian increments: the rank goes into the trajectory id."""
+        import torch.distributed as dist
+        return (dist.get_rank() << 40) if dist.is_available() and dist.is_initialized() else 0
+
+    def _device_step(self, state, action, f64, hit_rule, reward_type, dbt, source="numpy"):
         lib = L.load()
         in_dtype = state.dtype if not torch.is_tensor(state) else None
         grad_f32 = f64 and in_dtype == np.float32      # numpy promotion with a float32 state array (SURVEY App. A-5)
@@ -108,7 +127,8 @@ class _DoubleWellBase:
         env_c = L.make_env(self.d, self.alpha, self.sigma, self.dt, self.lb, self.rb, self.state_init.reshape(-1), hit_rule)
         rt = {"state-action": L.REWARD_STATE_ACTION, "state-action-next-state": L.REWARD_STATE_ACTION_NEXT_STATE}[reward_type]
         with torch.cuda.device(dev):
-            rc = lib.rlsde_env_step(env_c, K, _ptr(st), _ptr(ac), _ptr(db_in), int(self.rng_seed), 0, int(self._pass_counter),
+            rc = lib.rlsde_env_step(env_c, K, _ptr(st), _ptr(ac), _ptr(db_in), 0 if dbt is not None else self._noise_key(source),
+                                    self._rank_offset(), int(self._pass_counter),
                                     (L.F_STATE_F64 if f64 else 0) | (L.F_GRAD_F32 if grad_f32 else 0), rt, _ptr(nxt), _ptr(rew), _ptr(done), _ptr(db_out),
                                     torch.cuda.current_stream(dev).cuda_stream)
         L.check(rc, "rlsde_env_step")
@@ -140,7 +160,7 @@ class _DoubleWellBase:
     def step_torch(self, state, action, reward_type="state-action", dbt=None):
         """Torch-path pass (environments.py:201-226): float32; results come back on the input's device."""
         out_dev = state.device if torch.is_tensor(state) else torch.device("cpu")
-        nxt, rew, done, db = self._device_step(state, action, False, L.HIT_ALL_GE_LB, reward_type, dbt)
+        nxt, rew, done, db = self._device_step(state, action, False, L.HIT_ALL_GE_LB, reward_type, dbt, source="torch")
         return nxt.to(out_dev), rew.to(out_dev), done.to(out_dev), db.to(out_dev)
 
 

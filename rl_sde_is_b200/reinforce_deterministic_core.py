@@ -68,7 +68,7 @@ def sample_loss_vectorized(env, model, K, *, noise=None, seed=None, n_steps_lim=
 
 
 def _loss_and_grads_fused(env, model, K, *, noise=None, seed=None, n_steps_lim=10**6, tanh="precise", stoch_int="reference",
-                          ckpt_every=None, device=None, kernel="auto"):
+                          ckpt_every=None, device=None, kernel="auto", dist=None, tuning=None):
     """What ``sample_loss_vectorized`` + ``eff_loss.backward()`` produce, with one host synchronisation and without the
     autograd graph: sets ``p.grad`` of the policy's parameters and returns ``(loss float, return_fht, time_steps)``.
     Used by ``reinforce()``; results are those of the autograd route (same kernels, same arguments)."""
@@ -89,10 +89,10 @@ def _loss_and_grads_fused(env, model, K, *, noise=None, seed=None, n_steps_lim=1
         params_host = torch.cat([t.reshape(-1) for lin in linears for t in (lin.weight, lin.bias)]).to(torch.float32).numpy()
     stats, grad, G, T = R.rollout_loss_and_grad(env_c, mlp_c, params_host, int(K), seed=_next_seed(seed), n_steps_lim=n_steps_lim,
                                                 noise=noise, tanh=tanh, stoch_int=stoch_int, ckpt_every=ckpt_every,
-                                                device=dev, kernel=kernel)
-    if (T < 0).any():
-        raise L.RlsdeError(f"{int((T < 0).sum())} of {K} trajectories did not reach the target set within "
-                           f"{lim} passes; raise n_steps_lim")
+                                                device=dev, kernel=kernel, dist=dist, tuning=tuning)
+    if stats[L.ST_N_UNFINISHED] > 0:           # counted over ALL shards: every rank raises together, before touching .grad
+        raise L.RlsdeError(f"{int(stats[L.ST_N_UNFINISHED])} of {int(stats[L.ST_N])} trajectories did not reach the target set "
+                           f"within {lim} passes; raise n_steps_lim")
     g = torch.from_numpy(grad.copy())
     off = 0
     for lin in linears:
@@ -100,7 +100,7 @@ def _loss_and_grads_fused(env, model, K, *, noise=None, seed=None, n_steps_lim=1
             piece = g[off:off + t.numel()].view_as(t).to(t.dtype)
             t.grad = piece if t.grad is None else t.grad + piece
             off += t.numel()
-    return float(np.float32(stats[L.ST_SUM_LOSS] / K)), G.copy(), (T + 1).astype(np.float64)
+    return float(np.float32(stats[L.ST_SUM_LOSS] / stats[L.ST_N])), G.copy(), (T + 1).astype(np.float64)
 
 
 class _DeviceLoop:
@@ -109,7 +109,7 @@ class _DeviceLoop:
     ``flush()``.  Small batches only (warp-per-trajectory kernels: K <= 16 x SMs, hidden width 32)."""
 
     def __init__(self, env, model, K, lr, n_iterations, *, n_steps_lim=10**6, tanh="precise", stoch_int="reference", device=None,
-                 betas=(0.9, 0.999), eps=1e-8):
+                 betas=(0.9, 0.999), eps=1e-8, dist=None):
         self.lib = L.load()
         self.env, self.model, self.K, self.lr, self.betas, self.eps = env, model, int(K), float(lr), betas, float(eps)
         d, H = R.policy_shape(model)
@@ -121,8 +121,12 @@ class _DeviceLoop:
         self.theta = flat.to(dev)
         self.m, self.v = torch.zeros_like(self.theta), torch.zeros_like(self.theta)
         self.grad = torch.empty_like(self.theta)
+        # data parallel: K is this rank's shard of dist.K_global; one all-gather per iteration, enqueued on
+        # the rollout's stream between the reverse pass and the Adam kernel, so the loop stays free of host round trips
+        self.dist = dist if dist is not None and dist.world_size > 1 else None
+        self.P = int(self.lib.rlsde_param_count(self.mlp_c))
         cfg = L.RlsdeRolloutCfg()
-        cfg.K, cfg.traj_offset, cfg.K_global = self.K, 0, self.K
+        cfg.K, cfg.traj_offset, cfg.K_global = self.K, (dist.traj_offset if self.dist else 0), (dist.K_global if self.dist else self.K)
         cfg.n_steps_lim = int(n_steps_lim)
         cfg.flags = L.F_STORE_PATH | L.F_KERNEL_WARP | {"precise": 0, "fast": L.F_TANH_FAST}[tanh] \
             | {"reference": 0, "exact": L.F_STOCH_INT_EXACT}[stoch_int]
@@ -136,6 +140,9 @@ class _DeviceLoop:
         self.logStats = torch.zeros((n, L.RLSDE_NSTATS), dtype=torch.float64, device=dev)
         self.events = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
         self.ws = R._workspace(dev, self.K)
+        if self.dist:
+            self.row = torch.zeros(self.P + L.RLSDE_NSTATS, dtype=torch.float64, device=dev)
+            self.local_stats = torch.zeros(L.RLSDE_NSTATS, dtype=torch.float64, device=dev)
         self.done, self.read = 0, 0
         self.events[0].record(torch.cuda.current_stream(dev))
 
@@ -145,7 +152,7 @@ class _DeviceLoop:
             d, H = R.policy_shape(model)
             if H != 32 or d != env.d or not torch.cuda.is_available():
                 return False
-            if any(k in rollout_opts for k in ("noise", "dist", "ckpt_every", "seed")) or rollout_opts.get("kernel", "auto") == "thread":
+            if any(k in rollout_opts for k in ("noise", "ckpt_every", "seed")) or rollout_opts.get("kernel", "auto") == "thread":
                 return False
             lim = int(rollout_opts.get("n_steps_lim", 10**6))
             if int(K) * lim * d * 4 > (8 << 30):             # every state is kept for the reverse pass
@@ -160,12 +167,25 @@ class _DeviceLoop:
         self.cfg.seed = _next_seed(None) & 0xFFFFFFFFFFFFFFFF
         with torch.cuda.device(self.dev):
             stream = torch.cuda.current_stream(self.dev)
-            rc = self.lib.rlsde_reinforce_step(self.env_c, self.mlp_c, self.theta.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-                                               self.cfg, 0, self.lr, self.betas[0], self.betas[1], self.eps, i + 1,
-                                               self.logG[i].data_ptr(), self.S.data_ptr(), self.logT[i].data_ptr(),
-                                               self.path.data_ptr(), self.logStats[i].data_ptr(), self.grad.data_ptr(),
-                                               self.ws.data_ptr(), self.ws.numel(), stream.cuda_stream)
-            L.check(rc, "rlsde_reinforce_step")
+            if self.dist is None:
+                rc = self.lib.rlsde_reinforce_step(self.env_c, self.mlp_c, self.theta.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                                   self.cfg, 0, self.lr, self.betas[0], self.betas[1], self.eps, i + 1,
+                                                   self.logG[i].data_ptr(), self.S.data_ptr(), self.logT[i].data_ptr(),
+                                                   self.path.data_ptr(), self.logStats[i].data_ptr(), self.grad.data_ptr(),
+                                                   self.ws.data_ptr(), self.ws.numel(), stream.cuda_stream)
+                L.check(rc, "rlsde_reinforce_step")
+            else:
+                rc = self.lib.rlsde_reinforce_rollout(self.env_c, self.mlp_c, self.theta.data_ptr(), self.cfg, 0,
+                                                      self.logG[i].data_ptr(), self.S.data_ptr(), self.logT[i].data_ptr(),
+                                                      self.path.data_ptr(), self.local_stats.data_ptr(), self.grad.data_ptr(),
+                                                      self.row.data_ptr(), self.ws.data_ptr(), self.ws.numel(), stream.cuda_stream)
+                L.check(rc, "rlsde_reinforce_rollout")
+                rows = self.dist.all_gather_rows(self.row)            # the iteration's one collective, on this stream
+                rc = self.lib.rlsde_reinforce_apply(self.mlp_c, self.theta.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                                    rows.data_ptr(), int(rows.shape[0]), self.lr, self.betas[0], self.betas[1],
+                                                    self.eps, i + 1, self.grad.data_ptr(), self.logStats[i].data_ptr(),
+                                                    stream.cuda_stream)
+                L.check(rc, "rlsde_reinforce_apply")
             self.events[i + 1].record(stream)
         self.done = i + 1
 
@@ -184,12 +204,15 @@ class _DeviceLoop:
         G = self.logG[lo:hi].cpu().numpy()
         T = self.logT[lo:hi].cpu().numpy()
         st = self.logStats[lo:hi].cpu().numpy()
-        if (T < 0).any():
-            raise L.RlsdeError(f"{int((T < 0).sum())} trajectories did not reach the target set within {self.cfg.n_steps_lim} "
-                               "passes; raise n_steps_lim")
+        if (st[:, L.ST_N_UNFINISHED] > 0).any():
+            # such a batch took no Adam step on the device (adam_step_kernel looks at the count), so theta is that of the
+            # last complete iteration
+            bad = int(np.flatnonzero(st[:, L.ST_N_UNFINISHED] > 0)[0])
+            raise L.RlsdeError(f"iteration {lo + bad}: {int(st[bad, L.ST_N_UNFINISHED])} trajectories did not reach the target "
+                               f"set within {self.cfg.n_steps_lim} passes (no parameter update was applied); raise n_steps_lim")
         secs = np.array([self.events[i].elapsed_time(self.events[i + 1]) * 1e-3 for i in range(lo, hi)])
         self.read = hi
-        return lo, (st[:, L.ST_SUM_LOSS] / self.K).astype(np.float32), G, (T + 1).astype(np.float64), secs
+        return lo, (st[:, L.ST_SUM_LOSS] / st[:, L.ST_N]).astype(np.float32), G, (T + 1).astype(np.float64), secs
 
 
 class _LossWithAux(torch.autograd.Function):
@@ -245,6 +268,13 @@ def reinforce(env, gamma=1., d_hidden_layer=256, n_layers=3, batch_size=1000, lr
     from .approximate_methods import test_policy_vectorized
     from . import utils_path as up
 
+    # fail before any file is written if no fused kernel exists for this policy shape
+    if n_layers != 3:
+        raise L.RlsdeError(f"fused kernels cover n_layers=3 (two hidden layers, what the reference's CLI builds); got {n_layers}")
+    if not L.load().rlsde_supported(int(env.state_space_dim), int(d_hidden_layer), 2):
+        raise L.RlsdeError(f"no fused kernel for state dimension {env.state_space_dim} with hidden width {d_hidden_layer} "
+                           "(rlsde_supported)")
+
     rel_dir_path = None
     if save or load:
         rel_dir_path = up.get_reinforce_det_dir_path(env, agent="reinforce-deterministic", gamma=gamma,
@@ -254,6 +284,20 @@ def reinforce(env, gamma=1., d_hidden_layer=256, n_layers=3, batch_size=1000, lr
         return up.load_data(rel_dir_path)
     stored = up.load_data(rel_dir_path) if load else None
 
+    shard = rollout_opts.get("dist")
+    if shard is not None and shard.world_size > 1:
+        # data parallel: batch_size is the GLOBAL batch, every rank rolls its shard out.  All ranks must build the same
+        # initial policy and draw the same Philox keys (the global trajectory id makes the shards' noise disjoint), so
+        # an unseeded run takes rank 0's seed.
+        if shard.K_global != batch_size:
+            raise L.RlsdeError(f"dist.K_global ({shard.K_global}) must equal batch_size ({batch_size})")
+        if seed is None:
+            import torch.distributed as tdist
+            box = [int(torch.randint(0, 2**31 - 1, (1,)).item())]
+            tdist.broadcast_object_list(box, src=0, group=shard.group)
+            np.random.seed(box[0])
+            torch.manual_seed(box[0])
+    K_local = shard.K_local if shard is not None else batch_size
     if seed is not None:
         np.random.seed(seed)
         torch.manual_seed(seed)
@@ -264,7 +308,7 @@ def reinforce(env, gamma=1., d_hidden_layer=256, n_layers=3, batch_size=1000, lr
         optimizer = optim.Adam(model.parameters(), lr=lr, fused=True)     # one pass over the 6 small tensors (same update rule)
     except (TypeError, RuntimeError, ValueError):
         optimizer = optim.Adam(model.parameters(), lr=lr)
-    fused_path = rollout_opts.get("dist") is None and all(p.device.type == "cpu" for p in model.parameters())
+    fused_path = all(p.device.type == "cpu" for p in model.parameters())
     data = dict(gamma=gamma, n_layers=n_layers, d_hidden_layer=d_hidden_layer, batch_size=batch_size, lr=lr,
                 n_iterations=n_iterations, seed=seed, backup_freq_iterations=backup_freq_iterations, model=model)
     if load:
@@ -303,11 +347,11 @@ def reinforce(env, gamma=1., d_hidden_layer=256, n_layers=3, batch_size=1000, lr
         run_test(0)
 
     if device_loop is None:
-        device_loop = not load and _DeviceLoop.supported(env, model, batch_size, rollout_opts, rollout_opts.get("device"))
+        device_loop = not load and _DeviceLoop.supported(env, model, K_local, rollout_opts, rollout_opts.get("device"))
     loop = None
     if device_loop and not load and n_iterations > 0:
-        loop = _DeviceLoop(env, model, batch_size, lr, n_iterations,
-                           **{k: v for k, v in rollout_opts.items() if k in ("n_steps_lim", "tanh", "stoch_int", "device")})
+        loop = _DeviceLoop(env, model, K_local, lr, n_iterations,
+                           **{k: v for k, v in rollout_opts.items() if k in ("n_steps_lim", "tanh", "stoch_int", "device", "dist")})
 
     def drain():
         """Bring the device loop's finished iterations into the result arrays (one synchronisation)."""
@@ -334,9 +378,9 @@ def reinforce(env, gamma=1., d_hidden_layer=256, n_layers=3, batch_size=1000, lr
             t0 = time.time()
             optimizer.zero_grad()
             if fused_path:     # same kernels as sample_loss_vectorized + backward(), one host synchronisation
-                eff_loss, batch_returns, batch_time_steps = _loss_and_grads_fused(env, model, batch_size, **rollout_opts)
+                eff_loss, batch_returns, batch_time_steps = _loss_and_grads_fused(env, model, K_local, **rollout_opts)
             else:
-                eff_loss, batch_returns, batch_time_steps = sample_loss_vectorized(env, model, batch_size, **rollout_opts)
+                eff_loss, batch_returns, batch_time_steps = sample_loss_vectorized(env, model, K_local, **rollout_opts)
                 eff_loss.backward()
             optimizer.step()
             cts[i] = time.time() - t0          # wall clock of zero_grad -> loss -> backward -> step, like the reference's ct

@@ -25,14 +25,23 @@ def env_struct(env, hit_rule):
 
 
 def policy_linears(model):
-    """The nn.Linear layers of a reference-style policy (models.py:4-18 + DeterministicPolicy)."""
+    """The three nn.Linear layers of a reference-style policy (models.py:4-18 + DeterministicPolicy).
+
+    The fused kernels evaluate exactly ``Linear -> Tanh -> Linear -> Tanh -> Linear [-> Identity]``; any other stack
+    (another nonlinearity, an output activation, dropout, ...) would be computed wrongly without an error, so the
+    structure is checked positively."""
     seq = getattr(model, "policy", model)
-    linears = [m for m in seq.modules() if isinstance(m, torch.nn.Linear)]
-    acts = [m for m in seq.modules() if isinstance(m, (torch.nn.Tanh, torch.nn.ReLU, torch.nn.Sigmoid, torch.nn.ELU))]
-    if len(linears) != 3:
-        raise L.RlsdeError(f"fused kernels cover 2 hidden layers (n_layers=3, what the reference builds); got {len(linears)} Linear layers")
-    if not all(isinstance(a, torch.nn.Tanh) for a in acts):
-        raise L.RlsdeError("fused kernels cover Tanh hidden activations (what the reference uses)")
+    if not isinstance(seq, torch.nn.Sequential):
+        raise L.RlsdeError("the policy must be an nn.Sequential (or expose one as .policy), as built by models.mlp")
+    layers = [m for m in seq if not isinstance(m, torch.nn.Identity)]
+    want = (torch.nn.Linear, torch.nn.Tanh, torch.nn.Linear, torch.nn.Tanh, torch.nn.Linear)
+    if len(layers) != len(want) or not all(type(m) is w for m, w in zip(layers, want)):
+        got = " -> ".join(type(m).__name__ for m in seq)
+        raise L.RlsdeError("fused kernels cover Linear -> Tanh -> Linear -> Tanh -> Linear -> Identity "
+                           f"(n_layers=3 with Tanh, what the reference builds); got {got}")
+    linears = [layers[0], layers[2], layers[4]]
+    if any(lin.bias is None for lin in linears):
+        raise L.RlsdeError("fused kernels need Linear layers with bias (the reference's default)")
     return linears
 
 
@@ -104,7 +113,7 @@ class RolloutOut:
 
 def rollout_forward(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=10**6, noise=None, traj_offset=0,
                     K_global=None, tanh="precise", stoch_int="reference", state_f64=False, store_path=False,
-                    ckpt_every=1, policy_opt=None, grid=None, want_logw=True, device=None, out=None, kernel="auto"):
+                    ckpt_every=1, policy_opt=None, grid=None, want_logw=True, device=None, out=None, kernel="auto", tuning=None):
     """One launch of K1 for K trajectories.  ``params_host``: contiguous float32 numpy array (state_dict order)."""
     lib = L.load()
     dev = _cuda_device(device)
@@ -115,7 +124,7 @@ def rollout_forward(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=10**6, 
         raise L.RlsdeError(f"expected {lib.rlsde_param_count(mlp_c)} policy parameters, got {params_host.size}")
     flags = 0
     cfg = L.RlsdeRolloutCfg()
-    cfg.K, cfg.traj_offset, cfg.K_global = K, int(traj_offset), int(K_global if K_global is not None else K)
+    cfg.K, cfg.traj_offset, cfg.K_global = K, int(traj_offset), int(K_global if K_global is not None else int(traj_offset) + K)
     cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     cfg.n_steps_lim = int(n_steps_lim)
     if noise is not None:
@@ -153,6 +162,7 @@ def rollout_forward(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=10**6, 
         lo, hi, h = grid
         cfg.n_grid, cfg.grid_lo, cfg.grid_hi, cfg.grid_h = int(pol.numel()), float(lo), float(hi), float(h)
     cfg.flags = flags
+    L.apply_tuning(cfg, tuning)
     G = torch.empty(K, dtype=real, device=dev)
     S = torch.empty(K, dtype=real, device=dev)
     T = torch.empty(K, dtype=torch.int32, device=dev)
@@ -261,14 +271,16 @@ def rollout_backward(env_c, mlp_c, params_host, fwd: RolloutOut, loss_scale, *, 
 
 
 def rollout_loss_and_grad(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=10**6, noise=None, tanh="precise",
-                          stoch_int="reference", ckpt_every=1, device=None, kernel="auto", balance=True):
+                          stoch_int="reference", ckpt_every=1, device=None, kernel="auto", balance=True, tuning=None,
+                          dist=None):
     """One REINFORCE evaluation with a single host synchronisation: K1 (with checkpoints), the statistics reduction and
     K2 are enqueued back to back, and loss numerator, gradient, returns and hit indices come back in ONE device-to-host
     copy.  (The autograd route -- sample_loss_vectorized + .backward() -- synchronises after each kernel; at the
     reference's K = 100 those round trips cost as much as the kernels.)
 
     Returns ``(stats float64[RLSDE_NSTATS], grad float32[P] of mean_k(-G_k - sg(G_k) S_k), G float32[K], T int32[K])``
-    as NumPy arrays."""
+    as NumPy arrays.  With ``dist`` (a ``distributed.Shard``) the K trajectories are this rank's shard: statistics and
+    gradient are those of the global batch (one all-gather of the packed rows), G and T stay local."""
     lib = L.load()
     dev = _cuda_device(device)
     K = int(K)
@@ -287,13 +299,13 @@ def rollout_loss_and_grad(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=1
     S = torch.empty(K, dtype=torch.float32, device=dev)
     flags = L.F_STORE_PATH
     cfg = L.RlsdeRolloutCfg()
-    cfg.K, cfg.traj_offset, cfg.K_global = K, 0, K
+    cfg.K, cfg.traj_offset, cfg.K_global = K, (dist.traj_offset if dist is not None else 0), (dist.K_global if dist is not None else K)
     cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     cfg.n_steps_lim = int(n_steps_lim)
     if noise is not None:
         if noise.device != dev or noise.dtype != torch.float32 or not noise.is_contiguous() or noise.dim() != 3 \
-                or noise.shape[1] != K or noise.shape[2] != env_c.d:
-            raise L.RlsdeError(f"noise must be a contiguous float32 CUDA tensor [n_steps, {K}, {env_c.d}]")
+                or noise.shape[1] != cfg.K_global or noise.shape[2] != env_c.d:
+            raise L.RlsdeError(f"noise must be a contiguous float32 CUDA tensor [n_steps, {cfg.K_global}, {env_c.d}]")
         flags |= L.F_NOISE_INJECTED
         cfg.noise_steps = int(noise.shape[0])
     flags |= {"precise": 0, "fast": L.F_TANH_FAST}[tanh]
@@ -303,6 +315,7 @@ def rollout_loss_and_grad(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=1
     cfg.ckpt_every = int(ckpt_every)
     cfg.ckpt_stride = (lim_eff + cfg.ckpt_every - 1) // cfg.ckpt_every
     cfg.flags = flags
+    L.apply_tuning(cfg, tuning)
     path = torch.empty((K, cfg.ckpt_stride, env_c.d), dtype=torch.float32, device=dev)
     ws = _workspace(dev, K)
     with torch.cuda.device(dev):
@@ -314,8 +327,14 @@ def rollout_loss_and_grad(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=1
         thread_path = (flags & L.F_KERNEL_THREAD) or not ((flags & L.F_KERNEL_WARP) or K <= 16 * n_sm)
         order = torch.argsort(T, descending=True, stable=True) if balance and thread_path and K > 32 else None
         rc = lib.rlsde_rollout_bwd(env_c, mlp_c, params_host.ctypes.data, cfg, _ptr(noise), _ptr(G), _ptr(T), _ptr(path),
-                                   _ptr(order), 1.0 / K, _ptr(grad), _ptr(ws), ws.numel(), stream)
+                                   _ptr(order), 1.0 / cfg.K_global, _ptr(grad), _ptr(ws), ws.numel(), stream)
         L.check(rc, "rlsde_rollout_bwd")
+        if dist is not None and dist.world_size > 1:
+            # the iteration's ONE exchange: every rank's [gradient | statistics] row, added in rank order
+            from .distributed import pack_grad_and_stats, reduce_gathered
+            g_all, s_all = reduce_gathered(dist.all_gather_rows(pack_grad_and_stats(grad, stats)), P)
+            grad.copy_(g_all)
+            stats.copy_(s_all)
     host = pack.cpu().numpy()                               # the iteration's only synchronisation
     return (host[o_stats:o_stats + 128].view(np.float64), host[o_grad:o_grad + 4 * P].view(np.float32),
             host[o_G:o_G + 4 * K].view(np.float32), host[o_T:o_T + 4 * K].view(np.int32))

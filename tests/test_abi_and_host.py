@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(L.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert L.load().rlsde_version() == 100
+    assert L.load().rlsde_version() == 200
 
 
 def test_argument_validation_without_gpu():
