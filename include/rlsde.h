@@ -122,6 +122,9 @@ typedef struct rlsde_rollout_cfg {
                                    (-1 = never, 0 = automatic) */
   int64_t bwd_warp_share;       /* longest trajectories the reverse pass gives to the warp-per-trajectory kernel
                                    (-1 = none, 0 = automatic) */
+  int32_t bwd_kernel;           /* thread-per-trajectory reverse pass, hidden width 32: 0 = automatic (tensor-core kernel),
+                                   1 = tensor-core kernel (mma.sync, float16 x 3 split), 2 = CUDA-core kernel (FFMA2) */
+  int32_t reserved_;
 } rlsde_rollout_cfg;
 
 /* layout of a statistics record (double[RLSDE_NSTATS]); sums are over the K local trajectories,

@@ -21,6 +21,10 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 # A/B variants for kernel experiments: RLSDE_VARIANT=name RLSDE_NVCC_EXTRA="-DFOO=1" builds librlsde_b200_name.so
 # from its own object directory; select it at run time with RLSDE_LIB_PATH.
 VARIANT = os.environ.get("RLSDE_VARIANT", "")
+# RLSDE_VARIANT_ONLY=prefix[,prefix]: only the translation units whose name starts with one of the prefixes are rebuilt
+# with the variant's flags; all others are taken from the default build's object directory (fast A/B builds of one kernel)
+VARIANT_ONLY = [p for p in os.environ.get("RLSDE_VARIANT_ONLY", "").split(",") if p]
+BASE_OBJ_DIR = os.path.join(ROOT, "build", "obj")
 OBJ_DIR = os.path.join(ROOT, "build", "obj" + ("_" + VARIANT if VARIANT else ""))
 LIB_PATH = os.path.join(PKG_DIR, "librlsde_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
 ORACLE_DIR = os.path.join(ROOT, "oracle")
@@ -79,6 +83,9 @@ def build_cuda(force=False, verbose=False, jobs=None):
     todo, objs = [], []
     for f in sources:
         src = os.path.join(CSRC, f)
+        if VARIANT and VARIANT_ONLY and not any(f.startswith(p) for p in VARIANT_ONLY):
+            objs.append(os.path.join(BASE_OBJ_DIR, f[:-3] + ".o"))      # shared with the default build (must be up to date)
+            continue
         obj = os.path.join(OBJ_DIR, f[:-3] + ".o")
         stamp = obj + ".stamp"
         with open(src, "rb") as fh:

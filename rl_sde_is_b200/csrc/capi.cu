@@ -11,6 +11,7 @@
 #include "../../include/rlsde.h"
 #include "aux_kernels.cuh"
 #include "rollout_bwd.cuh"
+#include "rollout_bwd_mma.cuh"
 #include "rollout_warp.cuh"
 
 namespace rlsde {
@@ -18,6 +19,28 @@ namespace rlsde {
 static thread_local char g_last_cuda_error[256] = "";
 static std::atomic<long long> g_kernel_launches{0};
 void note_kernel_launches(int n) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Second stream for the reverse pass: the warp-per-trajectory kernel walks the longest trajectories of a large batch
+// while the thread-per-trajectory kernel works on the bulk (fork / join with events, so the caller's stream stays the
+// only one it has to think about; the pattern is legal inside CUDA graph capture).  One per host thread, created on first
+// use, never destroyed: the one piece of state the library keeps besides the last-error text.
+struct AuxStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int device = -1;
+  bool get() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (stream != nullptr && dev == device) return true;
+    if (stream != nullptr) { cudaStreamDestroy(stream); cudaEventDestroy(fork); cudaEventDestroy(join); stream = nullptr; }
+    if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) { stream = nullptr; return false; }
+    if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) { cudaStreamDestroy(stream); stream = nullptr; return false; }
+    device = dev;
+    return true;
+  }
+};
+static thread_local AuxStream g_aux;
 
 static int cuda_fail(cudaError_t e, const char* where) {
   snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", where, cudaGetErrorString(e));
@@ -336,23 +359,43 @@ int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
     if (n_long < 0) n_long = 0;
   }
   FwdArgs Abulk = A;
+  float* partial_aux = (float*)((char*)partial + bwd_partial_main_bytes());
+  // thread-per-trajectory family, hidden width 32: the tensor-core kernel (rollout_bwd_mma.cuh) unless the caller asks for
+  // the CUDA-core one (cfg.bwd_kernel == 2; kept for A/B measurements and as a second implementation in the tests)
+  // (state dimensions above 4 stay on the CUDA-core kernel unless asked: there the d-sized blocks of the tensor-core kernel
+  // spill -- d = 10: 39.8 ms against 28.4 ms at K = 2e5, profiles/r02/bwd_mma_variants.log)
+  const bool use_mma = mlp->d_hidden == MMA_H && (cfg->bwd_kernel == 1 || (cfg->bwd_kernel == 0 && env->d <= 4));
+  cudaEvent_t join = nullptr;
   if (n_long > 0) {
     FwdArgs Along = A;
     Along.K = n_long;
     Abulk.order = A.order + n_long;
     Abulk.K = A.K - n_long;
     Abulk.grad_accumulate = 1;
+    // the long trajectories run concurrently with the bulk on the second stream when the bulk's reduction can wait for
+    // them (tensor-core kernel); otherwise first, on the caller's stream
+    cudaStream_t s_long = stream;
+    if (use_mma && Abulk.K > 0 && g_aux.get()) {
+      if ((e = cudaEventRecord(g_aux.fork, stream)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord(fork)");
+      if ((e = cudaStreamWaitEvent(g_aux.stream, g_aux.fork, 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent(fork)");
+      s_long = g_aux.stream;
+    }
 #define X(D_, H_)                                                                                                   \
   if (env->d == D_ && mlp->d_hidden == H_ && H_ == WARP_H)                                                          \
-    lrc = launch_rollout_bwd_warp<D_>(params_host, nullptr, Along, (float)loss_scale, grad_dev, partial, sm, stream);
+    lrc = launch_rollout_bwd_warp<D_>(params_host, nullptr, Along, (float)loss_scale, grad_dev, partial_aux, sm, s_long);
     RLSDE_SHAPES(X)
 #undef X
     if (lrc != 0) return cuda_fail((cudaError_t)lrc, "rollout_bwd (long trajectories) launch");
+    if (s_long != stream) {
+      if ((e = cudaEventRecord(g_aux.join, s_long)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord(join)");
+      join = g_aux.join;
+    }
     lrc = Abulk.K > 0 ? -1 : 0;
   }
 #define X(D_, H_)                                                                                                          \
   if (env->d == D_ && mlp->d_hidden == H_ && Abulk.K > 0)                                                                  \
     lrc = (warp_path && H_ == WARP_H) ? launch_rollout_bwd_warp<D_>(params_host, nullptr, Abulk, (float)loss_scale, grad_dev, partial, sm, stream) \
+          : (use_mma && H_ == MMA_H)  ? launch_rollout_bwd_mma<D_>(params_host, Abulk, (float)loss_scale, grad_dev, partial, sm, stream, join)      \
                                       : launch_rollout_bwd<D_, H_>(params_host, Abulk, (float)loss_scale, grad_dev, partial, sm, stream);
   RLSDE_SHAPES(X)
 #undef X

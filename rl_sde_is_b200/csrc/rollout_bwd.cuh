@@ -29,7 +29,12 @@ namespace rlsde {
 constexpr int BWD_MAX_WARPS = 148 * 16;          // upper bound on warps in the backward grid
 constexpr int BWD_MAX_PARAMS = 4608;             // >= P for every compiled shape (d=2, H=64: 4482)
 constexpr int BWD_MAX_SEG = 32;                  // largest ckpt_every the backward pass accepts
-inline size_t bwd_workspace_bytes() { return (size_t)BWD_MAX_WARPS * BWD_MAX_PARAMS * sizeof(float); }
+// two disjoint partial areas: [0, A) for the thread-per-trajectory kernel (float or double partials of a shape with
+// P <= 2304 parameters at hidden width 32), [A, A + B) for the warp-per-trajectory kernel that takes the longest
+// trajectories concurrently on a second stream
+inline size_t bwd_partial_main_bytes() { return (size_t)BWD_MAX_WARPS * BWD_MAX_PARAMS * sizeof(float); }
+inline size_t bwd_partial_aux_bytes() { return (size_t)BWD_MAX_WARPS * (BWD_MAX_PARAMS / 2) * sizeof(float); }
+inline size_t bwd_workspace_bytes() { return bwd_partial_main_bytes() + bwd_partial_aux_bytes(); }
 
 // acc[o .. o+3] (4 packed accumulators) += h * {w0, w1, w2, w3} with packed weights in registers
 #define RLSDE_FMA2X4_REG(acc, o, h, w0, w1, w2, w3)                                                   \

@@ -847,3 +847,43 @@ def test_table_quadrature_path_against_exact_cdf_path(alpha, beta, dt, h):
     # slabs of the fast path are exactly the rows of the full tensor
     slab = compute_p_tensor_batch(env, device_out=True, sprime_range=(37, 211))
     assert torch.equal(slab, fast[37:211])
+
+
+# ------------------------------------------------------------------------------ tensor-core reverse pass
+@pytest.mark.parametrize("d,ckpt", [(1, 1), (1, 8), (2, 1), (3, 4), (10, 16)])
+def test_reverse_pass_tensor_core_kernel_matches_cuda_core_kernel(d, ckpt):
+    """K2m (mma.sync, float16 x 3 operand split, fp64 partials) against K2 (FFMA2) on the same forward rollout: the two are
+    independent implementations of the same recursion, so they agree to the rounding of fp32 sums of ~1e5 cancelling terms."""
+    from rl_sde_is_b200 import _lib as L, rollout as R
+    from rl_sde_is_b200.models import DeterministicPolicy
+    torch.manual_seed(4)
+    m = DeterministicPolicy(d, d, [32, 32], nn.Tanh())
+    m.policy[4].bias.data.fill_(0.8 if d == 1 else 3.0)
+    env = _make_env(d, 1.0, 1.0, 0.005)
+    params = R.flat_parameters(m).detach().numpy()
+    env_c, mlp_c = R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(d, 32)
+    K = 6000
+    fo = R.rollout_forward(env_c, mlp_c, params, K, seed=21, n_steps_lim=4000, store_path=True, ckpt_every=ckpt, want_logw=False,
+                           kernel="thread")
+    assert int(fo.stats[L.ST_N_UNFINISHED]) == 0
+    grads = {}
+    for name in ("mma", "ffma"):
+        fo.cfg.bwd_kernel = {"mma": 1, "ffma": 2}[name]
+        lib = L.load()
+        g = torch.empty(int(lib.rlsde_param_count(mlp_c)), dtype=torch.float32, device=fo.G.device)
+        ws = R._workspace(fo.G.device, K)
+        order = torch.argsort(fo.T, descending=True, stable=True)
+        rc = lib.rlsde_rollout_bwd(env_c, mlp_c, params.ctypes.data, fo.cfg, 0, fo.G.data_ptr(), fo.T.data_ptr(), fo.path.data_ptr(),
+                                   order.data_ptr(), 1.0 / K, g.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+        L.check(rc, "rlsde_rollout_bwd")
+        grads[name] = g.cpu().numpy().astype(np.float64)
+    scale = np.abs(grads["ffma"]).max()
+    assert scale > 0 and np.isfinite(grads["mma"]).all()
+    np.testing.assert_allclose(grads["mma"], grads["ffma"], rtol=0, atol=2e-4 * scale)
+    # and the tensor-core kernel is deterministic (static assignment, ordered reduction)
+    g2 = torch.empty_like(g)
+    fo.cfg.bwd_kernel = 1
+    rc = lib.rlsde_rollout_bwd(env_c, mlp_c, params.ctypes.data, fo.cfg, 0, fo.G.data_ptr(), fo.T.data_ptr(), fo.path.data_ptr(),
+                               order.data_ptr(), 1.0 / K, g2.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    L.check(rc, "rlsde_rollout_bwd")
+    assert np.array_equal(g2.cpu().numpy().astype(np.float64), grads["mma"])
