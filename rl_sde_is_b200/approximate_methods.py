@@ -77,10 +77,13 @@ def estimate_fht_vectorized(env, model, batch_size=int(1e5), k_max=10**7, *, noi
                             state_f64=True, device=None, dist=None):
     """Mean first hitting time ``mean(dt * k*)`` (reference :650-695).  NaN if a trajectory is unfinished
     (the reference would average uninitialised ``np.empty`` slots)."""
-    _, st = _numpy_path_rollout(env, model, batch_size, k_max, None, noise=noise, seed=seed, tanh=tanh, kernel=kernel,
-                                state_f64=state_f64, device=device, dist=dist)
+    out, st = _numpy_path_rollout(env, model, batch_size, k_max, None, noise=noise, seed=seed, tanh=tanh, kernel=kernel,
+                                  state_f64=state_f64, device=device, dist=dist)
     if st[L.ST_N_UNFINISHED] > 0:
         return np.nan
+    if dist is None:
+        # the reference's own expression, np.mean(dt * ep_fhts) with int32 hit indices (:695): identical rounding
+        return np.mean(env.dt * out.T.cpu().numpy())
     return np.float64(env.dt * st[L.ST_SUM_T] / st[L.ST_N])
 
 

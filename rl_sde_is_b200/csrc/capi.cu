@@ -13,6 +13,7 @@
 #include "rollout_bwd.cuh"
 #include "rollout_bwd_mma.cuh"
 #include "rollout_warp.cuh"
+#include "rollout_wide.cuh"
 
 namespace rlsde {
 
@@ -47,16 +48,25 @@ static int cuda_fail(cudaError_t e, const char* where) {
   return RLSDE_ERR_CUDA;
 }
 
-// shapes with compiled fused kernels: X(d, H)
-// (H = 64 compiles, but takes > 6 min per shape in the front end; it is left out of the default build)
+// shapes with compiled fused kernels: X(d, H).  Hidden width 32: the fully unrolled register / constant-bank kernels
+// (rollout_fwd.cuh, rollout_bwd*.cuh, rollout_warp.cuh).  Hidden widths 64 / 128 / 256 (the reference's reinforce()
+// default is 256): the tile kernels of rollout_wide.cuh, for the state dimensions the reference has environments for.
 #define RLSDE_SHAPES(X) X(1, 32) X(2, 32) X(3, 32) X(4, 32) X(10, 32)
+#define RLSDE_WIDE_SHAPES(X) X(1, 64) X(1, 128) X(1, 256) X(2, 64) X(2, 128) X(2, 256)
+
+static bool shape_is_wide(int d, int H) {
+#define X(D_, H_) if (d == D_ && H == H_) return true;
+  RLSDE_WIDE_SHAPES(X)
+#undef X
+  return false;
+}
 
 static bool shape_supported(int d, int H, int n_hidden) {
   if (n_hidden != 2) return false;
 #define X(D_, H_) if (d == D_ && H == H_) return true;
   RLSDE_SHAPES(X)
 #undef X
-  return false;
+  return shape_is_wide(d, H);
 }
 
 // kernel family for a call: latency kernels (warp per trajectory) for small batches, throughput kernels otherwise
@@ -187,7 +197,11 @@ int64_t rlsde_param_count(const rlsde_mlp* mlp) {
 }
 
 constexpr size_t WS_POLICY_BYTES = 16384;          // device copy of the packed policy (device-resident training step)
-static size_t ws_fixed_bytes() { return WS_COUNTER_BYTES + WS_STATS_BYTES + WS_POLICY_BYTES + bwd_workspace_bytes(); }
+constexpr size_t WS_WIDE_BYTES = (WIDE_PARAM_BYTES_MAX + 255) & ~(size_t)255;   // device image of a wide policy (rollout_wide.cuh)
+static size_t ws_fixed_bytes() { return WS_COUNTER_BYTES + WS_STATS_BYTES + WS_POLICY_BYTES + bwd_workspace_bytes() + WS_WIDE_BYTES; }
+static float* ws_wide_params(void* workspace_dev) {
+  return (float*)((char*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES + WS_POLICY_BYTES + bwd_workspace_bytes());
+}
 
 size_t rlsde_workspace_bytes(int64_t K) {
   const long long k = K > 0 ? K : 0;
@@ -240,6 +254,24 @@ static int rollout_fwd_impl(const rlsde_env* env, const rlsde_mlp* mlp, const fl
   cudaError_t e = cudaMemsetAsync(workspace_dev, 0, WS_COUNTER_BYTES, stream);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
   int lrc = -1;
+  if (shape_is_wide(env->d, mlp->d_hidden)) {
+    // wide policies: one kernel family (tiles of trajectories per block), no transition stream, no time slices
+    if (tr.base) return RLSDE_ERR_UNSUPPORTED;
+    if (workspace_bytes < ws_fixed_bytes()) return RLSDE_ERR_WORKSPACE;
+#define X(D_, H_) \
+  if (env->d == D_ && mlp->d_hidden == H_) lrc = launch_rollout_fwd_wide<D_, H_>(params_host, ws_wide_params(workspace_dev), A, sm, stream);
+    RLSDE_WIDE_SHAPES(X)
+#undef X
+    if (lrc != 0) return cuda_fail((cudaError_t)lrc, "rollout_fwd (wide) launch");
+    if (stats_dev) {
+      double* partial = (double*)((char*)workspace_dev + WS_COUNTER_BYTES);
+      const long long lim_eff = (A.flags & RLSDE_F_NOISE_INJECTED) && A.noise_steps < A.n_steps_lim ? A.noise_steps : A.n_steps_lim;
+      lrc = launch_reduce_stats(A.K, lim_eff, (A.flags & RLSDE_F_STATE_F64) != 0, G_dev, S_dev, T_dev, l2_dev, logw_dev,
+                                stats_dev, partial, stream);
+      if (lrc != 0) return cuda_fail((cudaError_t)lrc, "reduce_stats launch");
+    }
+    return RLSDE_OK;
+  }
   const bool warp_path = use_warp_kernels(A, mlp->d_hidden, sm, (A.flags & RLSDE_F_STORE_PATH) != 0);
   // ---- schedule of the thread-per-trajectory kernel (rollout_fwd.cuh).  Two ways to deal with the tail of a launch:
   //  * time slices (FIFO of continuation records, breadth-first): right when many trajectories run into the pass budget
@@ -345,6 +377,17 @@ int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
   float* partial = (float*)((char*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES + WS_POLICY_BYTES);
   int lrc = -1;
+  if (shape_is_wide(env->d, mlp->d_hidden)) {
+    if (A.ckpt_every != 1) return RLSDE_ERR_UNSUPPORTED;        // the wide reverse kernel reads every state from the path
+#define X(D_, H_)                                                                                                       \
+  if (env->d == D_ && mlp->d_hidden == H_)                                                                              \
+    lrc = launch_rollout_bwd_wide<D_, H_>(params_host, ws_wide_params(workspace_dev), A, (float)loss_scale, grad_dev, partial, \
+                                          bwd_partial_main_bytes(), sm, stream);
+    RLSDE_WIDE_SHAPES(X)
+#undef X
+    if (lrc != 0) return cuda_fail((cudaError_t)lrc, "rollout_bwd (wide) launch");
+    return RLSDE_OK;
+  }
   const bool warp_path = use_warp_kernels(A, mlp->d_hidden, sm, true);
   // Large batches with a length-sorted order: the reverse pass of a trajectory is sequential, and K2 walks a lone
   // trajectory at ~12 us per pass -- the longest few thousand trajectories, not the total work, set its run time (K = 4e5,

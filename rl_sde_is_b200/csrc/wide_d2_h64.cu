@@ -1,0 +1,3 @@
+// wide-policy rollout kernels (tile contraction through shared memory) for d = 2, hidden width = 64
+#include "rollout_wide_inst.cuh"
+RLSDE_INSTANTIATE_WIDE(2, 64)

@@ -50,7 +50,7 @@ def sample_loss_vectorized(env, model, K, *, noise=None, seed=None, n_steps_lim=
         noise = noise.to(device=dev, dtype=torch.float32).contiguous()
     lim = int(n_steps_lim) if noise is None else min(int(n_steps_lim), int(noise.shape[0]))
     if ckpt_every is None:
-        ckpt_every = R.choose_ckpt_every(int(K), d, lim)
+        ckpt_every = R.choose_ckpt_every(int(K), d, lim, hidden=H)
     opts = dict(seed=_next_seed(seed), n_steps_lim=n_steps_lim, noise=noise, tanh=tanh, stoch_int=stoch_int,
                 ckpt_every=ckpt_every, device=dev, kernel=kernel)
     if dist is not None:
@@ -83,7 +83,7 @@ def _loss_and_grads_fused(env, model, K, *, noise=None, seed=None, n_steps_lim=1
         noise = noise.to(device=dev, dtype=torch.float32).contiguous()
     lim = int(n_steps_lim) if noise is None else min(int(n_steps_lim), int(noise.shape[0]))
     if ckpt_every is None:
-        ckpt_every = R.choose_ckpt_every(int(K), d, lim)
+        ckpt_every = R.choose_ckpt_every(int(K), d, lim, hidden=H)
     linears = R.policy_linears(model)
     with torch.no_grad():
         params_host = torch.cat([t.reshape(-1) for lin in linears for t in (lin.weight, lin.bias)]).to(torch.float32).numpy()

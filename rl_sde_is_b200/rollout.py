@@ -340,8 +340,15 @@ def rollout_loss_and_grad(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=1
             host[o_G:o_G + 4 * K].view(np.float32), host[o_T:o_T + 4 * K].view(np.int32))
 
 
-def choose_ckpt_every(K, d, n_steps_lim, budget_bytes=8 << 30):
-    """Smallest checkpoint spacing whose path store fits the budget (1 = keep every state)."""
+def choose_ckpt_every(K, d, n_steps_lim, budget_bytes=8 << 30, hidden=32):
+    """Smallest checkpoint spacing whose path store fits the budget (1 = keep every state).  The wide-policy reverse
+    kernel (hidden width > 32) reads every state, so there the spacing is 1 or an error."""
+    if hidden != 32:
+        need = K * n_steps_lim * d * 4
+        if need > max(budget_bytes, 32 << 30):
+            raise L.RlsdeError(f"hidden width {hidden}: the reverse pass keeps every state (K={K} x n_steps_lim={n_steps_lim} x d={d} "
+                               f"floats = {need / 2**30:.1f} GiB); pass a smaller n_steps_lim")
+        return 1
     for c in (1, 2, 4, 8, 16, 32):
         if K * ((n_steps_lim + c - 1) // c) * d * 4 <= budget_bytes:
             return c

@@ -30,6 +30,12 @@ Fixtures (all arrays little-endian, names are the keys of the .npz):
                          (replay_buffers.py:7-88), noise recorded from ``env.step``: 1-D (finished and n_max-capped) and 2-D.
   formats.json           run-directory names of ``utils_path`` (:100-330) for the argument sets the tests use, and the
                          key/dtype/shape listing of an ``agent.npz`` written by the reference's ``reinforce`` (:102-336).
+  rollout_wide.npz       the torch and NumPy rollouts above for hidden widths 64, 128 and 256 (256 is the default of the
+                         reference's ``reinforce``, reinforce_deterministic_core.py:102), noise recorded.
+  rollout_long.npz       long / large cases whose noise is NOT stored: the reference draws it from ``torch.manual_seed(s)``
+                         / ``np.random.seed(s)`` streams (environments.py:145,208), which the tests replay call by call
+                         (``replay_torch_noise`` / ``replay_numpy_noise`` below): K = 256 with > 2 000-pass paths, and the
+                         metastable beta = 4, dt = 0.001 environment of BASELINE config 5.
   tables.npz             ``compute_r_table`` / ``compute_p_tensor_batch`` (dynamic_programming.py:3-36):
                          full tensors at h=0.1, strided sub-sample + checksums at h=0.01, and a
                          (alpha, beta) = (1, 4) case.
@@ -133,6 +139,99 @@ def numpy_rollout_case(am, env, model, K, seed, policy_opt, out, prefix):
         fht = am.estimate_fht_vectorized(env, model, batch_size=K)
     assert np.array_equal(rec2.stacked(), out[prefix + "noise"])
     out[prefix + "fht"] = np.array(fht, dtype=np.float64)
+
+
+def replay_torch_noise(seed, n_pass, K, d, dt):
+    """The increments ``env.step_torch`` draws (environments.py:208) after ``torch.manual_seed(seed)``: one
+    ``torch.randn((K, d))`` per pass, times ``sqrt(dt_tensor)`` in float32.  Shared by the tests (imported from here)."""
+    torch.manual_seed(seed)
+    sq = torch.sqrt(torch.tensor(dt, dtype=torch.float32))
+    return torch.stack([sq * torch.randn((K, d), dtype=torch.float32) for _ in range(n_pass)]).numpy()
+
+
+def replay_numpy_noise(seed, n_pass, K, d, dt):
+    """The increments ``env.step`` draws (environments.py:145) after ``np.random.seed(seed)``."""
+    np.random.seed(seed)
+    return np.stack([np.array(np.sqrt(dt) * np.random.randn(K, d), dtype=np.float32) for _ in range(n_pass)])
+
+
+def wide_cases(env1, env2, core, am):
+    out = {}
+    env = env1.DoubleWellStoppingTime1D(beta=1.0, alpha=1.0, dt=0.005)
+    env.discretize_state_space(0.05)
+    for tag, H, K, seed in (("h64_", 64, 8, 31), ("h128_", 128, 6, 32), ("h256_", 256, 6, 33)):
+        torch.manual_seed(100 + H)
+        model = core.DeterministicPolicy(1, 1, [H, H], nn.Tanh())
+        model.policy[4].bias.data.fill_(1.0)
+        torch_rollout_case(core, env, model, K, seed, out, "t" + tag)
+        policy_opt = (1.5 * np.cos(env.state_space_h) + 0.25).reshape(-1, 1)
+        numpy_rollout_case(am, env, model, K + 3, seed + 50, policy_opt, out, "n" + tag)
+    envd2 = env2.DoubleWellStoppingTime2D(beta=1.0, alpha=1.0, dt=0.005)
+    torch.manual_seed(7)
+    model = core.DeterministicPolicy(2, 2, [128, 128], nn.Tanh())
+    model.policy[4].bias.data.fill_(1.5)
+    torch_rollout_case(core, envd2, model, 5, 34, out, "t2d_h128_")
+    # the reference's reinforce() default shape at its own initialisation (near-null control: long paths), H = 256
+    torch.manual_seed(1)
+    model = core.DeterministicPolicy(1, 1, [256, 256], nn.Tanh())
+    torch_rollout_case(core, env, model, 4, 35, out, "tinit_h256_")
+    np.savez_compressed(os.path.join(OUT_DIR, "rollout_wide.npz"), **out)
+    print("wrote rollout_wide.npz")
+
+
+def long_cases(env1, env2, core, am):
+    """Cases too long to store their noise: the tests regenerate it from the seed (see replay_*_noise)."""
+    out = {}
+
+    def torch_case(env, model, K, seed, prefix):
+        torch.manual_seed(seed)
+        model.zero_grad()
+        with NoiseRecorder(env, "step_torch") as rec:
+            loss, return_fht, time_steps = core.sample_loss_vectorized(env, model, K)
+        loss.backward()
+        noise = rec.stacked()
+        assert np.array_equal(noise, replay_torch_noise(seed, noise.shape[0], K, env.d, env.dt)), "torch noise replay differs"
+        out[prefix + "seed"] = np.array([seed, K, noise.shape[0]], dtype=np.int64)
+        out[prefix + "loss"] = np.array(loss.detach().numpy())
+        out[prefix + "return_fht"] = return_fht.copy()
+        out[prefix + "time_steps"] = time_steps.copy()
+        put_params(out, prefix, model)
+        for k, p in model.named_parameters():
+            out[f"{prefix}grad.{k}"] = p.grad.detach().numpy().copy()
+        out[prefix + "env"] = np.array([env.d, float(np.ravel(env.alpha)[0]), env.beta, env.dt], dtype=np.float64)
+        print(f"  {prefix}: K={K} passes={noise.shape[0]} loss={float(loss):.8f} max T={time_steps.max()}")
+
+    def numpy_case(env, model, K, seed, policy_opt, prefix):
+        np.random.seed(seed)
+        with NoiseRecorder(env, "step") as rec:
+            res = am.test_policy_vectorized(env, model, batch_size=K, policy_opt=policy_opt)
+        noise = rec.stacked()
+        assert np.array_equal(noise, replay_numpy_noise(seed, noise.shape[0], K, env.d, env.dt)), "numpy noise replay differs"
+        out[prefix + "seed"] = np.array([seed, K, noise.shape[0]], dtype=np.int64)
+        out[prefix + "result"] = np.array(res, dtype=np.float64)
+        out[prefix + "policy_opt"] = policy_opt
+        put_params(out, prefix, model)
+        out[prefix + "env"] = np.array([env.d, float(np.ravel(env.alpha)[0]), env.beta, env.dt, env.h_state], dtype=np.float64)
+        print(f"  {prefix}: K={K} passes={noise.shape[0]} result={res}")
+
+    # K = 256, near-null initial policy (seed 1): the longest of 256 uncontrolled paths runs for thousands of passes
+    env = env1.DoubleWellStoppingTime1D(beta=1.0, alpha=1.0, dt=0.005)
+    env.discretize_state_space(0.05)
+    torch.manual_seed(1)
+    model = core.DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    torch_case(env, model, 256, 41, "t256_")
+    numpy_case(env, model, 256, 42, np.zeros((env.n_states, 1)), "n256_")
+    # metastable environment of config 5 (beta = 4, dt = 0.001) under a moderate constant push (the uncontrolled mean is
+    # 7e4 passes: too long for a CPU fixture)
+    envm = env1.DoubleWellStoppingTime1D(beta=4.0, alpha=1.0, dt=0.001)
+    envm.discretize_state_space(0.05)
+    torch.manual_seed(2)
+    model = core.DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    model.policy[4].bias.data.fill_(1.2)
+    torch_case(envm, model, 48, 43, "tmeta_")
+    numpy_case(envm, model, 48, 44, np.zeros((envm.n_states, 1)), "nmeta_")
+    np.savez_compressed(os.path.join(OUT_DIR, "rollout_long.npz"), **out)
+    print("wrote rollout_long.npz")
 
 
 def dp_sweeps(env1, dp):
@@ -258,6 +357,12 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "dp":      # regenerate only the DP-sweep fixture
         dp_sweeps(env1, dp)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "wide":    # only the wide-policy fixture
+        wide_cases(env1, env2, core, am)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "long":    # only the long-path fixture
+        long_cases(env1, env2, core, am)
         return
 
     # ---------------------------------------------------------------- torch path, 1-D

@@ -171,3 +171,40 @@ def test_replay_transitions_match_reference(golden, prefix):
         assert out[name].dtype == want.dtype and out[name].shape == want.shape, name
         assert np.array_equal(out[name], want), name
     assert np.array_equal(np.signbit(out["rewards"]), np.signbit(g[prefix + "rewards"]))      # the -0.0 of detecting passes
+
+
+# ------------------------------------------------------------------------------ round 2 fixtures: wide policies, long replays
+@pytest.mark.parametrize("prefix", ["th64_", "th256_", "t2d_h128_"])
+def test_wide_torch_rollout_matches_reference(golden, prefix):
+    torch.set_num_threads(1)
+    g = golden("rollout_wide")
+    d, alpha, beta, dt = _env(g, prefix)
+    out = ref.rollout_loss_torch(d, alpha, beta, dt, ref.params_from_npz(g, prefix), g[prefix + "noise"])
+    assert np.array_equal(out["time_steps"], g[prefix + "time_steps"].astype(np.int64))
+    assert np.array_equal(out["return_fht"], g[prefix + "return_fht"]) and out["loss"] == g[prefix + "loss"]
+    for k in ref.PARAM_KEYS:
+        np.testing.assert_allclose(out["grads"][k], g[f"{prefix}grad.{k}"], rtol=2e-5, atol=2e-7)
+
+
+@pytest.mark.parametrize("prefix", ["nh64_", "nh256_"])
+def test_wide_numpy_rollout_matches_reference(golden, prefix):
+    g = golden("rollout_wide")
+    e = g[prefix + "env"]
+    st = ref.rollout_stats_numpy(int(e[0]), float(e[1]), float(e[2]), float(e[3]), ref.params_from_npz(g, prefix), g[prefix + "noise"],
+                                 policy_opt=g[prefix + "policy_opt"], h_state=float(e[4]))
+    assert np.array_equal(np.array(ref.test_policy_result(st, True)), g[prefix + "result"])
+
+
+def test_long_replays_regenerate_their_noise_and_match_reference(golden):
+    """rollout_long.npz stores seeds, not noise: the reference's host generators are replayed call by call."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import replay_numpy_noise
+    g = golden("rollout_long")
+    for prefix, dt in (("n256_", 0.005), ("nmeta_", 0.001)):
+        seed, K, n_pass = (int(v) for v in g[prefix + "seed"])
+        e = g[prefix + "env"]
+        st = ref.rollout_stats_numpy(1, float(e[1]), float(e[2]), float(e[3]), ref.params_from_npz(g, prefix),
+                                     replay_numpy_noise(seed, n_pass, K, 1, dt), policy_opt=g[prefix + "policy_opt"], h_state=float(e[4]))
+        assert np.array_equal(np.array(ref.test_policy_result(st, True)), g[prefix + "result"])
