@@ -265,14 +265,15 @@ int rlsde_reduce_stats(int64_t K, int64_t n_steps_lim, uint32_t flags, const voi
  * For s outside the target set: Phi((x_s'+h-mu)/sd) - Phi((x_s'-h-mu)/sd) with the two tails
  * folded into rows 0 and Ns-1; for s in the target set: 1/|TS| if s' in TS else 0.
  * h_half is the bin half-width (the reference passes h_state / 2, dynamic_programming.py:34).
- * state_grid_uniform != 0: the caller asserts that the state grid is equally spaced (to ~1e-14); cells no wider than
- * 0.2 sd are then integrated by Gauss-Legendre quadrature with a density recurrence along s' (|error| < 1e-13)
- * instead of two erf/erfc evaluations per cell.  0 always takes the erf/erfc path.
+ * state_grid_uniform != 0: the caller asserts that the state grid is equally spaced (to ~1e-14) with spacing
+ * state_grid_step = (x_{Ns-1} - x_0) / (Ns - 1) (a host value: the recurrence constants derived from it travel as a
+ * kernel parameter); cells no wider than 0.2 sd are then integrated by Gauss-Legendre quadrature with a density
+ * recurrence along s' (|error| < 1e-13) instead of two erf/erfc evaluations per cell.  0 always takes the erf/erfc path.
  */
 int rlsde_tables(const double* state_grid_dev, int64_t Ns, const double* action_grid_dev, int64_t Na,
                  const uint8_t* in_ts_dev, int64_t n_ts, double alpha, double sigma, double dt, double h_half,
                  double lb, double rb, int64_t sprime_begin, int64_t sprime_end, double* P_dev, double* R_dev,
-                 int32_t state_grid_uniform, void* stream);
+                 int32_t state_grid_uniform, double state_grid_step, void* stream);
 
 /* column sums over s' of a P slab, accumulated into colsum_dev[Ns*Na] (check_p_tensor, tabular_dp_tables.py:15-17) */
 int rlsde_tables_colsum(const double* P_dev, int64_t n_sprime, int64_t Ns, int64_t Na, double* colsum_dev,

@@ -108,7 +108,7 @@ def load():
     lib.rlsde_rollout_bwd.argtypes = [C.POINTER(RlsdeEnv), C.POINTER(RlsdeMlp), vp, C.POINTER(RlsdeRolloutCfg),
                                       vp, vp, vp, vp, vp, dbl, vp, vp, C.c_size_t, vp]
     lib.rlsde_reduce_stats.argtypes = [i64, i64, u32, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
-    lib.rlsde_tables.argtypes = [vp, i64, vp, i64, vp, i64, dbl, dbl, dbl, dbl, dbl, dbl, i64, i64, vp, vp, i32, vp]
+    lib.rlsde_tables.argtypes = [vp, i64, vp, i64, vp, i64, dbl, dbl, dbl, dbl, dbl, dbl, i64, i64, vp, vp, i32, dbl, vp]
     lib.rlsde_tables_colsum.argtypes = [vp, i64, i64, i64, vp, vp]
     lib.rlsde_env_step.argtypes = [C.POINTER(RlsdeEnv), i64, vp, vp, vp, u64, i64, i64, u32, i32, vp, vp, vp, vp, vp]
     lib.rlsde_noise_fill.argtypes = [u64, i64, i64, i32, i64, i64, dbl, vp, vp]

@@ -38,7 +38,7 @@ int launch_env_step(const StepArgs& A, bool f64, cudaStream_t stream);
 int launch_tables(const double* state_grid, long long Ns, const double* action_grid, long long Na,
                   const unsigned char* in_ts, long long n_ts, double alpha, double sigma, double dt, double h_half,
                   double lb, double rb, long long sprime_begin, long long sprime_end, double* P, double* R,
-                  int uniform_grid, cudaStream_t stream);
+                  int uniform_grid, double grid_step, cudaStream_t stream);
 int launch_tables_colsum(const double* P, long long n_sprime, long long Ns, long long Na, double* colsum,
                          cudaStream_t stream);
 

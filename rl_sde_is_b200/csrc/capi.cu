@@ -549,13 +549,13 @@ int rlsde_reduce_stats(int64_t K, int64_t n_steps_lim, uint32_t flags, const voi
 int rlsde_tables(const double* state_grid_dev, int64_t Ns, const double* action_grid_dev, int64_t Na,
                  const uint8_t* in_ts_dev, int64_t n_ts, double alpha, double sigma, double dt, double h_half,
                  double lb, double rb, int64_t sprime_begin, int64_t sprime_end, double* P_dev, double* R_dev,
-                 int32_t state_grid_uniform, void* stream_) {
+                 int32_t state_grid_uniform, double state_grid_step, void* stream_) {
   if (!state_grid_dev || !action_grid_dev || !in_ts_dev || Ns < 1 || Na < 1 || Ns > 65535) return RLSDE_ERR_INVALID_ARG;
   if (sprime_begin < 0 || sprime_end > Ns || sprime_begin > sprime_end) return RLSDE_ERR_INVALID_ARG;
   if (!(dt > 0) || !(sigma > 0) || !(h_half > 0)) return RLSDE_ERR_INVALID_ARG;
   if (!P_dev && !R_dev) return RLSDE_ERR_INVALID_ARG;
   const int lrc = launch_tables(state_grid_dev, Ns, action_grid_dev, Na, in_ts_dev, n_ts, alpha, sigma, dt, h_half, lb, rb,
-                                sprime_begin, sprime_end, P_dev, R_dev, state_grid_uniform, (cudaStream_t)stream_);
+                                sprime_begin, sprime_end, P_dev, R_dev, state_grid_uniform, state_grid_step, (cudaStream_t)stream_);
   if (lrc != 0) return cuda_fail((cudaError_t)lrc, "tables launch");
   return RLSDE_OK;
 }

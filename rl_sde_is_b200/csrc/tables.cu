@@ -96,31 +96,43 @@ struct GlConst {
   double half_ds2;                         // ds^2 / 2
 };
 
+// host side: the constants of the recurrences are the same for every column; they travel as a kernel parameter (round 1
+// formed them once per block behind a barrier: 4.1 warps per issue slot stalled there, profiles/r01/ncu_tables_gl_v2.txt)
+static GlConst make_gl_const(double grid_step, double sigma, double dt, double h) {
+  GlConst C;
+  C.inv_sd = 1.0 / (sigma * sqrt(dt));
+  C.dcell = 2.0 * h * C.inv_sd;
+  C.dstep = grid_step * C.inv_sd;
+  C.rho = exp(-C.dstep * C.dstep);
+  C.half_ds2 = 0.5 * C.dstep * C.dstep;
+  C.off_a = 0.4305681557970263 * C.dcell;
+  C.off_b = 0.1699905217924281 * C.dcell;
+  C.coef_a = 2.0 * C.dcell * 0.1739274225687269 * exp(-0.5 * C.off_a * C.off_a);
+  C.coef_b = 2.0 * C.dcell * 0.3260725774312731 * exp(-0.5 * C.off_b * C.off_b);
+  C.sh_a = sinh(0.5 * C.off_a * C.dstep);
+  C.sh_b = sinh(0.5 * C.off_b * C.dstep);
+  C.mu_a = 4.0 * C.sh_a * C.sh_a;
+  C.mu_b = 4.0 * C.sh_b * C.sh_b;
+  C.eh_a = exp(0.5 * C.off_a * C.dstep);
+  C.eh_b = exp(0.5 * C.off_b * C.dstep);
+  return C;
+}
+
+// Stores.  A row of P has Ns Na entries and Ns Na is odd at config 3 (401 x 601), so consecutive rows start 72 bytes
+// apart modulo 128: a warp storing its 32 columns writes 256 bytes at 8-byte alignment, i.e. two partial 32-byte sectors
+// per store instruction on three rows out of four, and the SM-to-L2 write path -- not HBM -- is what saturates: 5.4 TB/s
+// here, 6.9 TB/s for the same kernel with an artificial Na = 608 (every row sector-aligned), 7.4 TB/s for a plain fill of
+// the tensor (tools/bench_tables_align.py, tools/bench_fill.py).  Three ways around the misalignment were built and
+// measured in round 2, all slower than storing straight from registers (0.143 ms): rows staged in shared memory and
+// stored rotated to sector boundaries (0.211 ms), rows staged and handed to the TMA unit as 1 KB bulk copies (UBLKCP;
+// 0.209 ms -- the staging loop with its two barriers per eight rows alone takes 0.146 ms), and one warp owning 128
+// columns, four per lane, rotated inside the warp with shuffles (0.160 ms; 112 registers).  Kept: the direct store.
 __global__ void __launch_bounds__(128) tables_gl_kernel(const double* __restrict__ sgrid, long long Ns,
                                                         const double* __restrict__ agrid, long long Na,
                                                         const unsigned char* __restrict__ in_ts, double inv_nts,
                                                         double alpha, double sigma, double dt, double h,
-                                                        long long sp_begin, long long sp_end, double* __restrict__ P) {
-  // constants of the recurrences: the same for every column, computed once per block from the grid end points
-  __shared__ GlConst C;
-  if (threadIdx.x == 0) {
-    C.inv_sd = 1.0 / (sigma * sqrt(dt));
-    C.dcell = 2.0 * h * C.inv_sd;
-    C.dstep = (sgrid[Ns - 1] - sgrid[0]) / (double)(Ns - 1) * C.inv_sd;
-    C.rho = exp(-C.dstep * C.dstep);
-    C.half_ds2 = 0.5 * C.dstep * C.dstep;
-    C.off_a = 0.4305681557970263 * C.dcell;
-    C.off_b = 0.1699905217924281 * C.dcell;
-    C.coef_a = 2.0 * C.dcell * 0.1739274225687269 * exp(-0.5 * C.off_a * C.off_a);
-    C.coef_b = 2.0 * C.dcell * 0.3260725774312731 * exp(-0.5 * C.off_b * C.off_b);
-    C.sh_a = sinh(0.5 * C.off_a * C.dstep);
-    C.sh_b = sinh(0.5 * C.off_b * C.dstep);
-    C.mu_a = 4.0 * C.sh_a * C.sh_a;
-    C.mu_b = 4.0 * C.sh_b * C.sh_b;
-    C.eh_a = exp(0.5 * C.off_a * C.dstep);
-    C.eh_b = exp(0.5 * C.off_b * C.dstep);
-  }
-  __syncthreads();
+                                                        long long sp_begin, long long sp_end, double* __restrict__ P,
+                                                        const __grid_constant__ GlConst C) {
   const long long stride = Ns * Na;
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= stride) return;
@@ -134,15 +146,20 @@ __global__ void __launch_bounds__(128) tables_gl_kernel(const double* __restrict
   if (sp_begin >= sp_end) return;
   double* out = P + (sp_begin - slab_begin) * stride + c;              // P points at row slab_begin
   if (in_ts[s]) {
-    for (long long sp = sp_begin; sp < sp_end; ++sp, out += stride) *out = in_ts[sp] ? inv_nts : 0.0;
+    for (long long sp = sp_begin; sp < sp_end; ++sp, out += stride) __stcs(out, in_ts[sp] ? inv_nts : 0.0);
     return;
   }
-  const double xs = sgrid[s];
-  const double act = agrid[a];
+  const double xs = __ldg(sgrid + s);
+  const double act = __ldg(agrid + a);
+  const double x_lo = __ldg(sgrid + chunk_lo);
+  const double inv_sd = C.inv_sd, rho = C.rho, mua = C.mu_a, mub = C.mu_b;
   const double grad = __dmul_rn(__dmul_rn(__dmul_rn(4.0, alpha), xs), __dsub_rn(__dmul_rn(xs, xs), 1.0));
   const double mu = __dadd_rn(xs, __dmul_rn(__dadd_rn(-grad, __dmul_rn(sigma, act)), dt));
+  // tails folded into the first and the last row of the grid (environments.py:97-101): formed up front, added in registers
+  const double tail_lo = sp_begin == 0 ? ndtr((__ldg(sgrid) - h - mu) * inv_sd) : 0.0;
+  const double tail_hi = sp_end == Ns ? 1.0 - ndtr((__ldg(sgrid + Ns - 1) + h - mu) * inv_sd) : 0.0;
   // anchors sit at absolute multiples of GL_ANCHOR, so a slab holds exactly the entries of the full tensor
-  const double m = fma(sgrid[chunk_lo] - h - mu, C.inv_sd, 0.5 * C.dcell);       // midpoint of cell chunk_lo
+  const double m = fma(x_lo - h - mu, inv_sd, 0.5 * C.dcell);       // midpoint of cell chunk_lo
   double phi = 0.3989422804014327 * exp(-0.5 * m * m);
   double r = exp(-fma(m, C.dstep, C.half_ds2));
   const double ea = exp(m * C.off_a), eb = exp(m * C.off_b);
@@ -151,25 +168,23 @@ __global__ void __launch_bounds__(128) tables_gl_kernel(const double* __restrict
   // first difference: cosh((m + ds) o) - cosh(m o) = 2 sinh((m + ds/2) o) sinh(ds o / 2)
   double da = C.coef_a * ((ea * C.eh_a - ia / C.eh_a) * C.sh_a);
   double db = C.coef_b * ((eb * C.eh_b - ib / C.eh_b) * C.sh_b);
-  const double rho = C.rho, mua = C.mu_a, mub = C.mu_b;
   for (long long sp = chunk_lo; sp < sp_begin; ++sp) {      // a slab that starts inside a chunk: advance without storing
     phi *= r; r *= rho;
     ya += da; da = fma(mua, ya, da);
     yb += db; db = fma(mub, yb, db);
   }
-  double* const first = out;
   const int n = (int)(sp_end - sp_begin);
 #pragma unroll 8
   for (int j = 0; j < n; ++j) {
-    *out = phi * (ya + yb);
+    double p = phi * (ya + yb);
+    if (j == 0) p += tail_lo;
+    if (j == n - 1) p += tail_hi;
+    __stcs(out, p);                         // streaming store: the tensor is written once and is larger than L2
     out += stride;
     phi *= r; r *= rho;
     ya += da; da = fma(mua, ya, da);
     yb += db; db = fma(mub, yb, db);
   }
-  // tails folded into the first and the last row of the grid (environments.py:97-101)
-  if (sp_begin == 0) *first += ndtr((sgrid[0] - h - mu) * C.inv_sd);
-  if (sp_end == Ns) *(out - stride) += 1.0 - ndtr((sgrid[Ns - 1] + h - mu) * C.inv_sd);
 }
 
 __global__ void rtable_kernel(long long Ns, const double* __restrict__ agrid, long long Na,
@@ -185,15 +200,16 @@ __global__ void rtable_kernel(long long Ns, const double* __restrict__ agrid, lo
 int launch_tables(const double* state_grid, long long Ns, const double* action_grid, long long Na,
                   const unsigned char* in_ts, long long n_ts, double alpha, double sigma, double dt, double h_half,
                   double lb, double rb, long long sprime_begin, long long sprime_end, double* P, double* R,
-                  int uniform_grid, cudaStream_t stream) {
+                  int uniform_grid, double grid_step, cudaStream_t stream) {
   (void)lb; (void)rb;
   const double dcell = 2.0 * h_half / (sigma * sqrt(dt));
-  if (P && sprime_end > sprime_begin && uniform_grid && Ns >= 2 && dcell <= 0.2) {
+  if (P && sprime_end > sprime_begin && uniform_grid && grid_step > 0.0 && Ns >= 2 && dcell <= 0.2 ) {
     const long long n_chunks = (sprime_end - 1) / GL_ANCHOR - sprime_begin / GL_ANCHOR + 1;
     const long long cols = Ns * Na;
     dim3 grid((unsigned)((cols + 127) / 128), (unsigned)n_chunks);
     tables_gl_kernel<<<grid, 128, 0, stream>>>(state_grid, Ns, action_grid, Na, in_ts, n_ts > 0 ? 1.0 / (double)n_ts : 0.0,
-                                               alpha, sigma, dt, h_half, sprime_begin, sprime_end, P);
+                                               alpha, sigma, dt, h_half, sprime_begin, sprime_end, P,
+                                               make_gl_const(grid_step, sigma, dt, h_half));
     note_kernel_launches(1);
   } else if (P && sprime_end > sprime_begin) {
     const long long nsp = sprime_end - sprime_begin;

@@ -53,7 +53,8 @@ def _tables(env, want_p, want_r, device, sprime_range=None, exact_cdf=False, out
     with torch.cuda.device(dev):
         rc = lib.rlsde_tables(_ptr(sg), Ns, _ptr(ag), Na, _ptr(ts), int(env.is_in_ts.sum()), float(env.alpha),
                               float(env.sigma), float(env.dt), float(env.h_state) / 2.0, float(env.lb), float(env.rb),
-                              lo, hi, _ptr(P), _ptr(Rt), uniform, torch.cuda.current_stream(dev).cuda_stream)
+                              lo, hi, _ptr(P), _ptr(Rt), uniform, float((grid[-1] - grid[0]) / (Ns - 1)) if Ns >= 2 else 0.0,
+                              torch.cuda.current_stream(dev).cuda_stream)
     L.check(rc, "rlsde_tables")
     return P, Rt
 

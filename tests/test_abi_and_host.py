@@ -39,7 +39,7 @@ def test_argument_validation_without_gpu():
     # unsupported shape and null pointers are rejected before any CUDA call
     assert lib.rlsde_rollout_fwd(env, L.make_mlp(1, 48), None, cfg, *([None] * 9), None, 0, None) == -2
     assert lib.rlsde_rollout_fwd(env, L.make_mlp(1, 32), None, cfg, *([None] * 9), None, 0, None) == -1
-    assert lib.rlsde_tables(None, 4, None, 4, None, 1, 1.0, 1.0, 0.1, 0.1, 1.0, 2.0, 0, 4, None, None, 0, None) == -1
+    assert lib.rlsde_tables(None, 4, None, 4, None, 1, 1.0, 1.0, 0.1, 0.1, 1.0, 2.0, 0, 4, None, None, 0, 0.0, None) == -1
     assert lib.rlsde_noise_fill(0, 0, 4, 99, 0, 1, 0.1, None, None) == -1
 
 
