@@ -141,6 +141,13 @@ def _gloo_worker(rank, world, port, K_global, q):
     rec[L.ST_MAX_T] = 100.0 + rank                  # the maximum entry must be max-reduced, everything else summed
     rec = sh.all_reduce_stats(rec)
     assert float(rec[L.ST_MAX_T]) == 100.0 + world - 1 and float(rec[L.ST_N]) == K_global
+    # the training path's exchange: ONE all-gather of [gradient | statistics] rows, added in rank order by every rank
+    stats2 = stats.clone()
+    stats2[L.ST_MAX_T] = 7.0 + 3 * rank
+    rows = sh.all_gather_rows(D.pack_grad_and_stats(grad, stats2))
+    assert rows.shape == (world, 3 + L.RLSDE_NSTATS)
+    g2, s2 = D.reduce_gathered(rows, 3)
+    assert torch.equal(g2, g) and float(s2[L.ST_N]) == K_global and float(s2[L.ST_MAX_T]) == 7.0 + 3 * (world - 1)
     q.put((rank, sh.traj_offset, sh.K_local, g.tolist(), float(s[L.ST_N]), float(s[L.ST_SUM_G])))
     dist.destroy_process_group()
 

@@ -93,3 +93,32 @@ def test_hjb_solution_properties(beta):
     # 0.00543 at beta = 4, dt = 0.001, profiles/r01) sit a few per cent below because discrete monitoring misses crossings
     expect = {1.0: 0.164016, 4.0: 0.005496}[beta]
     assert abs(fine.psi_at(-1.0) - expect) / expect < 1e-4
+
+
+@pytest.mark.parametrize("beta", [1.0, 4.0])
+def test_hjb_solution_against_an_independent_integrator(beta):
+    """Pin for hjb_1d (the reference's sde_hjb_solver is not installed): the same boundary value problem solved by SHOOTING
+    with an adaptive Runge-Kutta integrator (scipy solve_ivp; the equation is linear, so one forward integration from the
+    Neumann end, normalised at the target set, is the solution) agrees with the finite-difference solve, and the latter
+    converges at second order in the grid spacing."""
+    from scipy.integrate import solve_ivp
+    from rl_sde_is_b200.hjb_1d import HJBSolution1D
+    env = SimpleNamespace(beta=beta, alpha=1.0, lb=1.0, sigma=np.sqrt(2.0 / beta))
+    x_min = -3.0
+
+    def rhs(x, y):          # y = (Psi, Psi');  (1/beta) Psi'' = V'(x) Psi' + Psi
+        return [y[1], beta * (4.0 * x * (x * x - 1.0) * y[1] + y[0])]
+
+    pts = np.array([-1.5, -1.0, -0.5, 0.0, 0.5, 0.9])
+    sol = solve_ivp(rhs, (x_min, 1.0), [1.0, 0.0], method="DOP853", rtol=1e-12, atol=1e-300, dense_output=True)
+    psi_rk = sol.sol(pts)[0] / sol.y[0, -1]
+    u_rk = env.sigma * sol.sol(pts)[1] / sol.sol(pts)[0]
+    errs = []
+    for h in (4e-3, 2e-3, 1e-3):
+        fd = HJBSolution1D(env, h=h, x_min=x_min)
+        errs.append(np.abs(fd.psi_at(pts) - psi_rk).max() / psi_rk.max())
+    assert errs[-1] < 2e-6
+    assert 3.5 < errs[0] / errs[1] < 4.5 and 3.5 < errs[1] / errs[2] < 4.5          # second order
+    fine = HJBSolution1D(env, h=5e-4, x_min=x_min)
+    np.testing.assert_allclose(fine.psi_at(pts), psi_rk, rtol=2e-6)
+    np.testing.assert_allclose(fine.u_opt_at(pts), u_rk, rtol=2e-4)

@@ -217,3 +217,30 @@ def test_drop_ins_accept_the_reference_objects():
     assert np.abs(compute_p_tensor_batch(env) - P_ref).max() < 1e-13
     assert np.array_equal(compute_r_table(env), R_ref)
     assert R.tables.check_p_tensor(env, compute_p_tensor_batch(env))
+
+
+# ------------------------------------------------------------------------------ HJB reference solution vs the IS estimator
+def test_hjb_psi_lies_inside_the_importance_sampling_estimate():
+    """Second pin for hjb_1d: Psi(-1) = E[exp(-tau)] from the finite-difference solve against the GPU importance-sampling
+    estimator of the same quantity.  The Euler-Maruyama estimate monitors the target set at discrete times and
+    is biased low by O(sqrt(dt)); two step sizes a factor 4 apart are extrapolated to dt -> 0, and the HJB value must lie
+    within the extrapolation's confidence interval (plus 0.5 % for the next-order term)."""
+    from types import SimpleNamespace
+    from rl_sde_is_b200.approximate_methods import is_estimate
+    from rl_sde_is_b200.hjb_1d import HJBSolution1D
+    from rl_sde_is_b200.models import DeterministicPolicy
+    torch.manual_seed(1)
+    model = DeterministicPolicy(1, 1, [32, 32], nn.Tanh())
+    model.policy[4].bias.data.fill_(0.6)                       # a mild push: smaller relative error than the null control
+    K = 2_000_000
+    est = {}
+    for dt in (0.004, 0.001):
+        env = _make_env(1, 1.0, 1.0, dt)
+        r = is_estimate(env, model, K, n_steps_lim=400000, seed=123)
+        assert r["n_unfinished"] == 0
+        est[dt] = (r["is_mean"], r["is_mean"] * r["is_rel_error"] / np.sqrt(K))
+    psi0 = 2.0 * est[0.001][0] - est[0.004][0]                 # bias ~ c sqrt(dt): sqrt(0.004) = 2 sqrt(0.001)
+    se = np.sqrt(4.0 * est[0.001][1] ** 2 + est[0.004][1] ** 2)
+    hjb = float(HJBSolution1D(SimpleNamespace(beta=1.0, alpha=1.0, lb=1.0, sigma=np.sqrt(2.0)), h=5e-4).psi_at(-1.0))
+    assert est[0.004][0] < est[0.001][0] < hjb                 # discrete monitoring misses crossings: biased low, less so at small dt
+    assert abs(psi0 - hjb) < 4.0 * se + 5e-3 * hjb, (psi0, hjb, se)
