@@ -57,9 +57,9 @@ class Shard:
         algorithm NCCL picks, and the maximum entry of the statistics record survives the exchange."""
         if self.world_size <= 1:
             return row.reshape(1, -1)
-        out = torch.empty((self.world_size, row.numel()), dtype=row.dtype, device=row.device)
-        dist.all_gather_into_tensor(out, row.contiguous(), group=self.group)
-        return out
+        out = torch.empty(self.world_size * row.numel(), dtype=row.dtype, device=row.device)
+        dist.all_gather_into_tensor(out, row.contiguous().reshape(-1), group=self.group)
+        return out.view(self.world_size, row.numel())
 
     @classmethod
     def from_env(cls, K_global, group=None):

@@ -55,8 +55,9 @@ def main():
     assert abs(loss_p - loss_w) <= 2e-6 * abs(loss_w)
     scale = float(g_whole.abs().max())
     assert float((g_part - g_whole).abs().max()) <= 2e-5 * scale, float((g_part - g_whole).abs().max()) / scale
-    gathered = [torch.empty_like(g_part) for _ in range(world)]
-    dist.all_gather(gathered, g_part.to(dev))
+    g_dev = g_part.to(dev)
+    gathered = [torch.empty_like(g_dev) for _ in range(world)]
+    dist.all_gather(gathered, g_dev)
     assert all(torch.equal(gathered[0], t) for t in gathered)                       # every rank formed the same bits
 
     # ---- device-resident training loop, data parallel: identical parameters on both ranks, close to the single-GPU run
