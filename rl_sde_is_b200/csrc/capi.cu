@@ -14,6 +14,7 @@
 #include "rollout_bwd_mma.cuh"
 #include "rollout_warp.cuh"
 #include "rollout_wide.cuh"
+#include "rollout_umma.cuh"
 
 namespace rlsde {
 
@@ -53,6 +54,7 @@ static int cuda_fail(cudaError_t e, const char* where) {
 // default is 256): the tile kernels of rollout_wide.cuh, for the state dimensions the reference has environments for.
 #define RLSDE_SHAPES(X) X(1, 32) X(2, 32) X(3, 32) X(4, 32) X(10, 32)
 #define RLSDE_WIDE_SHAPES(X) X(1, 64) X(1, 128) X(1, 256) X(2, 64) X(2, 128) X(2, 256)
+#define RLSDE_UMMA_SHAPES(X) X(1, 128) X(1, 256) X(2, 128) X(2, 256)
 
 static bool shape_is_wide(int d, int H) {
 #define X(D_, H_) if (d == D_ && H == H_) return true;
@@ -198,7 +200,13 @@ int64_t rlsde_param_count(const rlsde_mlp* mlp) {
 
 constexpr size_t WS_POLICY_BYTES = 16384;          // device copy of the packed policy (device-resident training step)
 constexpr size_t WS_WIDE_BYTES = (WIDE_PARAM_BYTES_MAX + 255) & ~(size_t)255;   // device image of a wide policy (rollout_wide.cuh)
-static size_t ws_fixed_bytes() { return WS_COUNTER_BYTES + WS_STATS_BYTES + WS_POLICY_BYTES + bwd_workspace_bytes() + WS_WIDE_BYTES; }
+constexpr size_t WS_UMMA_BYTES = 256 * 256 * 4;     // float16 hi / lo image of W2 streamed by the tcgen05 forward kernel (H = 256)
+static size_t ws_fixed_bytes() {
+  return WS_COUNTER_BYTES + WS_STATS_BYTES + WS_POLICY_BYTES + bwd_workspace_bytes() + WS_WIDE_BYTES + WS_UMMA_BYTES;
+}
+static uint8_t* ws_umma_image(void* workspace_dev) {
+  return (uint8_t*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES + WS_POLICY_BYTES + bwd_workspace_bytes() + WS_WIDE_BYTES;
+}
 static float* ws_wide_params(void* workspace_dev) {
   return (float*)((char*)workspace_dev + WS_COUNTER_BYTES + WS_STATS_BYTES + WS_POLICY_BYTES + bwd_workspace_bytes());
 }
@@ -258,10 +266,23 @@ static int rollout_fwd_impl(const rlsde_env* env, const rlsde_mlp* mlp, const fl
     // wide policies: one kernel family (tiles of trajectories per block), no transition stream, no time slices
     if (tr.base) return RLSDE_ERR_UNSUPPORTED;
     if (workspace_bytes < ws_fixed_bytes()) return RLSDE_ERR_WORKSPACE;
+    // hidden width 128 / 256 with enough trajectories for 128-row tiles on at least half the SMs: the tcgen05 kernel
+    // (rollout_umma.cuh); otherwise -- and always at width 64 -- the CUDA-core tile kernel (rollout_wide.cuh).
+    // cfg.wide_kernel: 1 forces tcgen05, 2 forces the CUDA-core kernel.
+    const bool umma_shape = mlp->d_hidden == 128 || mlp->d_hidden == 256;
+    const bool use_umma = umma_shape && (cfg->wide_kernel == 1 || (cfg->wide_kernel == 0 && A.K >= (long long)sm * UMMA_M / 2));
+    if (use_umma) {
+#define X(D_, H_)                                                                                                          \
+  if (env->d == D_ && mlp->d_hidden == H_)                                                                                 \
+    lrc = launch_rollout_fwd_umma<D_, H_>(params_host, ws_wide_params(workspace_dev), ws_umma_image(workspace_dev), A, sm, stream);
+      RLSDE_UMMA_SHAPES(X)
+#undef X
+    } else {
 #define X(D_, H_) \
   if (env->d == D_ && mlp->d_hidden == H_) lrc = launch_rollout_fwd_wide<D_, H_>(params_host, ws_wide_params(workspace_dev), A, sm, stream);
-    RLSDE_WIDE_SHAPES(X)
+      RLSDE_WIDE_SHAPES(X)
 #undef X
+    }
     if (lrc != 0) return cuda_fail((cudaError_t)lrc, "rollout_fwd (wide) launch");
     if (stats_dev) {
       double* partial = (double*)((char*)workspace_dev + WS_COUNTER_BYTES);

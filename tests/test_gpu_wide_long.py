@@ -244,3 +244,50 @@ def test_hjb_psi_lies_inside_the_importance_sampling_estimate():
     hjb = float(HJBSolution1D(SimpleNamespace(beta=1.0, alpha=1.0, lb=1.0, sigma=np.sqrt(2.0)), h=5e-4).psi_at(-1.0))
     assert est[0.004][0] < est[0.001][0] < hjb                 # discrete monitoring misses crossings: biased low, less so at small dt
     assert abs(psi0 - hjb) < 4.0 * se + 5e-3 * hjb, (psi0, hjb, se)
+
+
+# ------------------------------------------------------------------------------ tcgen05 forward kernel (rollout_umma.cuh)
+@pytest.mark.parametrize("prefix", ["th128_", "th256_", "t2d_h128_", "tinit_h256_"])
+def test_tcgen05_forward_matches_reference(golden, monkeypatch, prefix):
+    """The tensor-core forward kernel (float16 hi/lo operand split, fp32 accumulation in tensor memory) on the reference's
+    recorded noise: hit passes exact, returns / loss within 1e-5, and -- since the reverse pass reads its checkpoints -- the
+    reference's gradient."""
+    monkeypatch.setenv("RLSDE_WIDE_KERNEL", "umma")
+    g = golden("rollout_wide")
+    _check_torch_case(g, prefix, g[prefix + "noise"])
+
+
+@pytest.mark.parametrize("prefix", ["nh128_", "nh256_"])
+def test_tcgen05_forward_numpy_path_matches_reference(golden, monkeypatch, prefix):
+    monkeypatch.setenv("RLSDE_WIDE_KERNEL", "umma")
+    g = golden("rollout_wide")
+    _check_numpy_case(g, prefix, g[prefix + "noise"])
+
+
+@pytest.mark.parametrize("H", [128, 256])
+def test_tcgen05_forward_agrees_with_cuda_core_kernel(H):
+    """Same Philox stream through both wide forward kernels (tiles of 128 on the tensor cores / tiles of 32 on the CUDA
+    cores): the policies are evaluated to fp32-level accuracy by both, so almost every trajectory hits on the same pass with
+    the same return; the statistics agree closely.  Lane refill (more trajectories than tile slots) is exercised."""
+    from rl_sde_is_b200 import _lib as L, rollout as R
+    from rl_sde_is_b200.models import DeterministicPolicy
+    torch.manual_seed(6)
+    m = DeterministicPolicy(1, 1, [H, H], nn.Tanh())
+    m.policy[4].bias.data.fill_(0.9)
+    env = _make_env(1, 1.0, 1.0, 0.005)
+    params = R.flat_parameters(m).detach().numpy()
+    env_c, mlp_c = R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(1, H)
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    K = 128 * n_sm * 2 + 333
+    a = R.rollout_forward(env_c, mlp_c, params, K, seed=3, n_steps_lim=4000, tuning={"wide_kernel": "umma"})
+    b = R.rollout_forward(env_c, mlp_c, params, K, seed=3, n_steps_lim=4000, tuning={"wide_kernel": "ffma"})
+    Ta, Tb = a.T.cpu().numpy(), b.T.cpu().numpy()
+    same = Ta == Tb
+    assert same.mean() > 0.995 and (Ta >= 0).all()
+    np.testing.assert_allclose(a.G.cpu().numpy()[same], b.G.cpu().numpy()[same], rtol=2e-5)
+    np.testing.assert_allclose(a.S.cpu().numpy()[same], b.S.cpu().numpy()[same], rtol=2e-3, atol=2e-5)
+    sa, sb = a.stats, b.stats
+    assert abs(sa[L.ST_SUM_G] - sb[L.ST_SUM_G]) < 2e-4 * abs(sb[L.ST_SUM_G])
+    # determinism and independence of the launch shape: a shard of the same global batch reproduces its slice bit for bit
+    c = R.rollout_forward(env_c, mlp_c, params, 5000, seed=3, n_steps_lim=4000, traj_offset=700, K_global=K, tuning={"wide_kernel": "umma"})
+    assert torch.equal(c.T, a.T[700:5700]) and torch.equal(c.G, a.G[700:5700])

@@ -11,6 +11,7 @@ from rl_sde_is_b200.models import DeterministicPolicy
 ap = argparse.ArgumentParser()
 ap.add_argument("--H", type=int, default=256); ap.add_argument("--K", type=int, default=200000)
 ap.add_argument("--Ktrain", type=int, default=20000); ap.add_argument("--ref", action="store_true")
+ap.add_argument("--wide", default="auto", help="forward kernel at H = 128 / 256: auto | umma | ffma"); ap.add_argument("--no-train", action="store_true")
 a = ap.parse_args()
 H = a.H
 env = DoubleWellStoppingTime1D(beta=1.0, alpha=1.0, dt=0.005)
@@ -23,14 +24,14 @@ env_n, env_t, mlp_c = R.env_struct(env, L.HIT_X0_IN_LB_RB), R.env_struct(env, L.
 for it in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    out = R.rollout_forward(env_n, mlp_c, params, a.K, seed=it, n_steps_lim=1000, stoch_int="exact")
+    out = R.rollout_forward(env_n, mlp_c, params, a.K, seed=it, n_steps_lim=1000, stoch_int="exact", tuning={"wide_kernel": a.wide})
     e1.record(); torch.cuda.synchronize()
 u = float(out.stats[L.ST_USEFUL_STEPS]); ms = e0.elapsed_time(e1)
-print(json.dumps({"what": "forward test rollout", "H": H, "K": a.K, "ms": ms, "steps_per_s": u / ms * 1e3, "fp32_frac": u / ms * 1e3 * F_fwd / 74.45e12,
+print(json.dumps({"what": "forward test rollout", "kernel": a.wide, "H": H, "K": a.K, "ms": ms, "steps_per_s": u / ms * 1e3, "fp32_frac": u / ms * 1e3 * F_fwd / 74.45e12,
                   "flop_per_step": F_fwd}))
 m.policy[4].bias.data.fill_(0.5)
 params = R.flat_parameters(m).detach().numpy()
-for Kt in (1000, a.Ktrain):
+for Kt in (() if a.no_train else (1000, a.Ktrain)):
     for it in range(2):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record()
