@@ -5,12 +5,13 @@
 // Same semantics, Philox stream and outputs as K1 / K1x (rollout_fwd.cuh, rollout_wide.cuh).  One CTA of 192 threads per
 // SM advances a tile of 128 trajectories in lock step:
 //   warps 0-3  one THREAD per trajectory (= one TMEM lane).  Per pass the thread evaluates layer 1 for its own state
-//              (H FMAs + H tanh), splits the activations into float16 hi + lo and writes its row of the A operand into
-//              shared memory in the K-major core-matrix layout tcgen05 reads (8 rows x 16 bytes, no swizzle); after the
-//              MMAs it reads its row of the accumulator back (tcgen05.ld 32x32b: 32 columns per instruction), applies
-//              bias + tanh and sums the head in registers -- no cross-thread reduction anywhere -- and runs the
-//              environment pass with K1's arithmetic (traj_owner.cuh).  Finished trajectories are replaced from the
-//              global work counter (lane refill), so the tile stays full until the batch runs out.
+//              (H FMAs + H tanh) sixteen units at a time, splits the activations into float16 hi + lo and writes its row
+//              of that k-step's A operand into a ring of shared-memory slots in the K-major core-matrix layout tcgen05
+//              reads (8 rows x 16 bytes, no swizzle) -- the MMAs of a k-step start as soon as its slot is full, so layer 1
+//              overlaps the tensor pipe; after the MMAs it reads its row of the accumulator back (tcgen05.ld 32x32b: 32
+//              columns per instruction), applies bias + tanh and sums the head in registers -- no cross-thread reduction
+//              anywhere -- and runs the environment pass with K1's arithmetic (traj_owner.cuh).  Finished trajectories
+//              are replaced from the global work counter (lane refill), so the tile stays full until the batch runs out.
 //   warp 4     lane 0 issues the MMAs: per 16-wide k-step D += A_hi B_hi + A_lo B_hi + A_hi B_lo (M = 128, N = H, K = 16,
 //              kind::f16, fp32 accumulate): float16 hi + lo carry 22 significand bits per operand, the dropped lo x lo
 //              term is ~2^-22 -- fp32-level accuracy (rollout_bwd_mma.cuh has the error budget).  tcgen05.commit hands
@@ -19,8 +20,10 @@
 //              shared-memory image of the B operand by the host) does not fit beside A at H = 256 (2 x 128 KB), so every
 //              pass it travels L2 -> shared memory again, one cp.async.bulk of H x 64 bytes per k-step through a ring of
 //              four mbarrier-guarded stages.  128 trajectories share each byte.
-// Synchronisation is mbarriers only (a_ready: 128 arrivals; acc_ready: tcgen05.commit; full / empty per stage) plus one
-// __syncthreads_or per pass for the "any trajectory left?" vote.
+// Synchronisation is mbarriers only (a_full: 128 arrivals per slot, a_empty / empty / acc_ready: tcgen05.commit; full:
+// the bulk copy's transaction count) plus one __syncthreads_or per pass for the "any trajectory left?" vote.  A CTA needs
+// 100 KB of shared memory and H tensor-memory columns, so TWO CTAs share an SM: while one is in its accumulator-readback
+// phase (MUFU-bound) the other's MMAs keep the tensor pipe busy.
 #pragma once
 #include <cuda_fp16.h>
 #include "rollout_bwd_mma.cuh"     // f32 <-> f16 host helpers, split_pair
@@ -31,14 +34,16 @@ namespace rlsde {
 
 constexpr int UMMA_M = 128;                 // trajectories per tile = TMEM lanes
 constexpr int UMMA_THREADS = 192;
-constexpr int UMMA_STAGES = 4;
+constexpr int UMMA_STAGES = 4;                // weight stages (one k-step of B, hi + lo, each)
+constexpr int UMMA_ASLOTS = 4;                // activation slots (one k-step of A, hi + lo, each)
+constexpr uint32_t UMMA_ACHUNK = UMMA_M * 16 * 2 * 2;   // bytes of one A slot: 128 rows x 16 halfs, hi + lo
 
 template <int H> __host__ __device__ constexpr size_t umma_chunk_bytes() { return (size_t)H * 64; }        // hi + lo of one k-step
 template <int H> __host__ __device__ constexpr size_t umma_image_bytes() { return umma_chunk_bytes<H>() * (H / 16); }
 template <int D, int H>
 __host__ __device__ constexpr size_t umma_smem_bytes() {
-  // A hi + A lo, the weight ring, the small layers (W1t [D][H], b1, b2, W3 [D][H])
-  return 2 * (size_t)UMMA_M * H * 2 + UMMA_STAGES * umma_chunk_bytes<H>() + (size_t)(2 * D + 2) * H * sizeof(float);
+  // the A ring, the weight ring, the small layers (W1t [D][H], b1, b2, W3 [D][H])
+  return (size_t)UMMA_ASLOTS * UMMA_ACHUNK + UMMA_STAGES * umma_chunk_bytes<H>() + (size_t)(2 * D + 2) * H * sizeof(float);
 }
 
 // host: W2 (pre-scaled like MlpConst / WideParams: w2s[out * H + in]) -> the B-operand image streamed by the kernel.
@@ -115,23 +120,21 @@ __device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }  // namespace umma
 
 template <int D, int H, bool F64, bool FAST>
-__global__ void __launch_bounds__(UMMA_THREADS, 1) rollout_fwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict__ Bimg,
+__global__ void __launch_bounds__(UMMA_THREADS, 2) rollout_fwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict__ Bimg,
                                                                            const __grid_constant__ FwdArgs A) {
   using namespace umma;
   typedef WideParams<D, H> L;
   constexpr int KSTEPS = H / 16;
   constexpr uint32_t CHUNK = (uint32_t)umma_chunk_bytes<H>();
-  constexpr uint32_t A_BYTES = UMMA_M * H * 2;                  // one of A hi / A lo
   extern __shared__ __align__(128) uint8_t umma_smem[];
   uint8_t* const smem = umma_smem;
-  uint8_t* sAh = smem;
-  uint8_t* sAl = smem + A_BYTES;
-  uint8_t* sB = smem + 2 * A_BYTES;
+  uint8_t* sA = smem;                                           // UMMA_ASLOTS x [hi 4 KB | lo 4 KB]
+  uint8_t* sB = smem + UMMA_ASLOTS * UMMA_ACHUNK;
   float* sW1 = reinterpret_cast<float*>(sB + UMMA_STAGES * CHUNK);     // [D][H]
   float* sb1 = sW1 + D * H;
   float* sb2 = sb1 + H;
   float* sW3 = sb2 + H;                                                // [D][H]
-  __shared__ __align__(8) uint64_t full[UMMA_STAGES], empty[UMMA_STAGES], a_ready, acc_ready;
+  __shared__ __align__(8) uint64_t full[UMMA_STAGES], empty[UMMA_STAGES], a_full[UMMA_ASLOTS], a_empty[UMMA_ASLOTS], acc_ready;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool inject = (A.flags & RLSDE_F_NOISE_INJECTED) != 0;
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) rollout_fwd_umma_kernel(const
   }
   if (tid == 0) {
     for (int s = 0; s < UMMA_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(&a_ready, UMMA_M);
+    for (int s = 0; s < UMMA_ASLOTS; ++s) { mbar_init(&a_full[s], UMMA_M); mbar_init(&a_empty[s], 1); }
     mbar_init(&acc_ready, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -185,38 +188,47 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) rollout_fwd_umma_kernel(const
     const uint32_t par = pass & 1u;
 
     if (owner) {
-      // ---- layer 1 for this thread's trajectory -> its row of A (hi / lo), 8 units = one 16-byte core-matrix row at a time
+      // ---- layer 1 for this thread's trajectory -> its row of A (hi / lo), one k-step (16 units = two 16-byte core-matrix
+      // rows) per ring slot; the issuer starts the k-step's MMAs as soon as all 128 rows of the slot are in
       float xf[D];
 #pragma unroll
       for (int k = 0; k < D; ++k) xf[k] = (float)T.x[k];
       const uint32_t row_off = (uint32_t)((tid >> 3) * 128 + (tid & 7) * 16);
-#pragma unroll 4
-      for (int kc = 0; kc < H / 8; ++kc) {
-        float h[8];
+#pragma unroll 1
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        const unsigned c = pass * KSTEPS + ks;                    // running k-step index
+        const int slot = c % UMMA_ASLOTS;
+        if (c >= UMMA_ASLOTS) mbar_wait(&a_empty[slot], ((c / UMMA_ASLOTS) - 1u) & 1u);   // the MMAs that read it have completed
+        uint8_t* dst = sA + (size_t)slot * UMMA_ACHUNK + row_off;
 #pragma unroll
-        for (int q4 = 0; q4 < 2; ++q4) {
-          const float4 bb = *reinterpret_cast<const float4*>(sb1 + 8 * kc + 4 * q4);
-          float zz[4] = {bb.x, bb.y, bb.z, bb.w};
+        for (int kc2 = 0; kc2 < 2; ++kc2) {
+          const int kc = 2 * ks + kc2;
+          float h[8];
 #pragma unroll
-          for (int k = 0; k < D; ++k) {
-            const float4 ww = *reinterpret_cast<const float4*>(sW1 + k * H + 8 * kc + 4 * q4);
-            zz[0] = fmaf(xf[k], ww.x, zz[0]); zz[1] = fmaf(xf[k], ww.y, zz[1]);
-            zz[2] = fmaf(xf[k], ww.z, zz[2]); zz[3] = fmaf(xf[k], ww.w, zz[3]);
+          for (int q4 = 0; q4 < 2; ++q4) {
+            const float4 bb = *reinterpret_cast<const float4*>(sb1 + 8 * kc + 4 * q4);
+            float zz[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+              const float4 ww = *reinterpret_cast<const float4*>(sW1 + k * H + 8 * kc + 4 * q4);
+              zz[0] = fmaf(xf[k], ww.x, zz[0]); zz[1] = fmaf(xf[k], ww.y, zz[1]);
+              zz[2] = fmaf(xf[k], ww.z, zz[2]); zz[3] = fmaf(xf[k], ww.w, zz[3]);
+            }
+            tanh_pair<FAST>(pack2(zz[0], zz[1]), h[4 * q4], h[4 * q4 + 1]);
+            tanh_pair<FAST>(pack2(zz[2], zz[3]), h[4 * q4 + 2], h[4 * q4 + 3]);
           }
-          tanh_pair<FAST>(pack2(zz[0], zz[1]), h[4 * q4], h[4 * q4 + 1]);
-          tanh_pair<FAST>(pack2(zz[2], zz[3]), h[4 * q4 + 2], h[4 * q4 + 3]);
+          uint4 hi, lo;
+          split_pair(h[0], h[1], hi.x, lo.x);
+          split_pair(h[2], h[3], hi.y, lo.y);
+          split_pair(h[4], h[5], hi.z, lo.z);
+          split_pair(h[6], h[7], hi.w, lo.w);
+          const uint32_t off = (uint32_t)kc2 * (UMMA_M / 8) * 128;
+          *reinterpret_cast<uint4*>(dst + off) = hi;
+          *reinterpret_cast<uint4*>(dst + UMMA_ACHUNK / 2 + off) = lo;
         }
-        uint4 hi, lo;
-        split_pair(h[0], h[1], hi.x, lo.x);
-        split_pair(h[2], h[3], hi.y, lo.y);
-        split_pair(h[4], h[5], hi.z, lo.z);
-        split_pair(h[6], h[7], hi.w, lo.w);
-        const uint32_t off = (uint32_t)kc * (UMMA_M / 8) * 128 + row_off;
-        *reinterpret_cast<uint4*>(sAh + off) = hi;
-        *reinterpret_cast<uint4*>(sAl + off) = lo;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(&a_full[slot]);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
-      mbar_arrive(&a_ready);
 
       // ---- accumulator row -> h2 = tanh(z2 + b2) -> head, all in this thread's registers
       mbar_wait(&acc_ready, par);
@@ -248,24 +260,24 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) rollout_fwd_umma_kernel(const
       if (T.alive) T.pass(A, u, lim);
     } else if (warp == 4) {
       if (lane == 0) {
-        mbar_wait(&a_ready, par);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         constexpr uint32_t idesc = make_idesc(UMMA_M, H);
 #pragma unroll 1
         for (int ks = 0; ks < KSTEPS; ++ks) {
-          const unsigned c = pass * KSTEPS + ks;                  // running chunk index
-          const int s = c % UMMA_STAGES;
+          const unsigned c = pass * KSTEPS + ks;                  // running k-step index
+          const int s = c % UMMA_STAGES, slot = c % UMMA_ASLOTS;
+          mbar_wait(&a_full[slot], (c / UMMA_ASLOTS) & 1u);       // (also orders the previous pass's accumulator reads first)
           mbar_wait(&full[s], (c / UMMA_STAGES) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_off = (uint32_t)ks * 2 * (UMMA_M / 8) * 128;
-          const uint64_t ah = make_desc(smem_u32(sAh) + a_off, (UMMA_M / 8) * 128, 128);
-          const uint64_t al = make_desc(smem_u32(sAl) + a_off, (UMMA_M / 8) * 128, 128);
+          const uint32_t a_base = smem_u32(sA) + (uint32_t)slot * UMMA_ACHUNK;
+          const uint64_t ah = make_desc(a_base, (UMMA_M / 8) * 128, 128);
+          const uint64_t al = make_desc(a_base + UMMA_ACHUNK / 2, (UMMA_M / 8) * 128, 128);
           const uint64_t bh = make_desc(smem_u32(sB) + (uint32_t)s * CHUNK, (H / 8) * 128, 128);
           const uint64_t bl = make_desc(smem_u32(sB) + (uint32_t)s * CHUNK + CHUNK / 2, (H / 8) * 128, 128);
           mma_f16(tmem_base, ah, bh, idesc, ks > 0 ? 1u : 0u);
           mma_f16(tmem_base, al, bh, idesc, 1u);
           mma_f16(tmem_base, ah, bl, idesc, 1u);
-          commit(&empty[s]);                                      // the stage is free once these MMAs have read it
+          commit(&a_empty[slot]);                                 // both rings get their slot back once these MMAs have read it
+          commit(&empty[s]);
         }
         commit(&acc_ready);
       }

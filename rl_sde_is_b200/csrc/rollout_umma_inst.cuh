@@ -11,7 +11,13 @@ static int launch_fwd_umma_variant(const float* params_dev, const uint8_t* image
   const size_t smem = umma_smem_bytes<D, H>();
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  long long grid = sm_count;                                   // one CTA per SM (shared memory and tensor memory are per CTA)
+  // two CTAs per SM when shared memory and tensor memory allow (100 KB, H <= 256 columns each): one reads its accumulator
+  // back while the other's MMAs run
+  // (the occupancy query answers 1 under the default carveout, so the carveout is requested and the count derived here)
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  int per_sm = (2 * (smem + 2048) <= (size_t)227 * 1024) ? 2 : 1;
+  if (per_sm > 512 / H) per_sm = 512 / H;                      // tensor memory: 512 columns per SM
+  long long grid = (long long)sm_count * per_sm;
   const long long need = (args.K + UMMA_M - 1) / UMMA_M;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
