@@ -73,6 +73,8 @@ typedef enum rlsde_status {
 #define RLSDE_F_KERNEL_THREAD (1u << 8)   /* force the throughput kernels (one trajectory per thread) */
 #define RLSDE_F_KERNEL_WARP (1u << 9)     /* force the latency kernels (one trajectory per warp; hidden width 32, and for the
                                             reverse pass ckpt_every == 1).  Default: chosen from K (small batches -> warp) */
+#define RLSDE_F_KERNEL_TENSOR (1u << 10)  /* force the tile kernel with the hidden-hidden layer on the tensor cores (tcgen05; one
+                                            thread per trajectory, 128-trajectory tiles).  Default: large batches with a bounded pass budget */
 #define RLSDE_F_GRAD_F32 (1u << 5)       /* rlsde_env_step with RLSDE_F_STATE_F64: the caller's state array was float32.  numpy then
                                             evaluates grad V in float32 in the 1-D env (python-float alpha), and state**2 - 1 in
                                             float32 in the d-D env (float64 alpha array)   */

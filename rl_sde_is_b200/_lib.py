@@ -25,6 +25,7 @@ F_STORE_PATH = 1 << 4
 F_GRAD_F32 = 1 << 5
 F_KERNEL_THREAD = 1 << 8
 F_KERNEL_WARP = 1 << 9
+F_KERNEL_TENSOR = 1 << 10
 REWARD_STATE_ACTION = 0
 REWARD_STATE_ACTION_NEXT_STATE = 1
 

@@ -55,6 +55,7 @@ static int cuda_fail(cudaError_t e, const char* where) {
 #define RLSDE_SHAPES(X) X(1, 32) X(2, 32) X(3, 32) X(4, 32) X(10, 32)
 #define RLSDE_WIDE_SHAPES(X) X(1, 64) X(1, 128) X(1, 256) X(2, 64) X(2, 128) X(2, 256)
 #define RLSDE_UMMA_SHAPES(X) X(1, 128) X(1, 256) X(2, 128) X(2, 256)
+#define RLSDE_UMMA_NARROW_SHAPES(X) X(1, 32) X(2, 32) X(3, 32) X(4, 32) X(10, 32)
 
 static bool shape_is_wide(int d, int H) {
 #define X(D_, H_) if (d == D_ && H == H_) return true;
@@ -294,6 +295,37 @@ static int rollout_fwd_impl(const rlsde_env* env, const rlsde_mlp* mlp, const fl
     return RLSDE_OK;
   }
   const bool warp_path = use_warp_kernels(A, mlp->d_hidden, sm, (A.flags & RLSDE_F_STORE_PATH) != 0);
+  // ---- hidden width 32 on the tensor cores (rollout_umma.cuh with resident weights: tiles of 128 trajectories, one thread
+  // per trajectory, lane refill).  The per-pass work of a warp drops from ~1 290 to ~860 instructions; like K1 it ends up
+  // bound by the MUFU pipe (71 % busy with the two-MUFU tanh: profiles/r02/ncu_rollout_fwd_umma_h32_v1.txt).  Measured at
+  // 1e6 trajectories, budget 1 000 passes (tools/bench_fwd_kernels.py): d = 1 precise tanh 27.5 ms against K1's 25.1 ms,
+  // fast tanh 20.6 against 21.5; d = 2: 54.5 % of the FP32 roofline against 52 %; d = 4: 58.1 % against 53.4 %; d = 10:
+  // 50.9 % against 44.9 %.  It has no breadth-first schedule, so its launch ends with a tail of (longest trajectory) x
+  // (~1 us per pass).  Automatic where it wins: d >= 2 or the fast tanh, large batches, a bounded pass budget -- and never
+  // when the caller pins a kernel family or a schedule of the thread-per-trajectory kernel.
+  {
+    const long long lim_eff = (A.flags & RLSDE_F_NOISE_INJECTED) && A.noise_steps < A.n_steps_lim ? A.noise_steps : A.n_steps_lim;
+    const bool forced = (A.flags & RLSDE_F_KERNEL_TENSOR) != 0;
+    const bool pinned = (A.flags & (RLSDE_F_KERNEL_THREAD | RLSDE_F_KERNEL_WARP)) != 0 || cfg->fwd_quantum != 0 || cfg->fwd_handoff != 0;
+    const bool automatic = !pinned && !warp_path && A.K >= (long long)sm * UMMA_M * 2 && lim_eff <= 4096 &&
+                           (env->d >= 2 || (A.flags & RLSDE_F_TANH_FAST) != 0);
+    if (mlp->d_hidden == 32 && !tr.base && (forced || automatic)) {
+      if (workspace_bytes < ws_fixed_bytes()) return RLSDE_ERR_WORKSPACE;
+#define X(D_, H_)                                                                                                          \
+  if (env->d == D_ && mlp->d_hidden == H_)                                                                                 \
+    lrc = launch_rollout_fwd_umma<D_, H_>(params_host, ws_wide_params(workspace_dev), ws_umma_image(workspace_dev), A, sm, stream);
+      RLSDE_UMMA_NARROW_SHAPES(X)
+#undef X
+      if (lrc != 0) return cuda_fail((cudaError_t)lrc, "rollout_fwd (tensor) launch");
+      if (stats_dev) {
+        double* partial = (double*)((char*)workspace_dev + WS_COUNTER_BYTES);
+        lrc = launch_reduce_stats(A.K, lim_eff, (A.flags & RLSDE_F_STATE_F64) != 0, G_dev, S_dev, T_dev, l2_dev, logw_dev,
+                                  stats_dev, partial, stream);
+        if (lrc != 0) return cuda_fail((cudaError_t)lrc, "reduce_stats launch");
+      }
+      return RLSDE_OK;
+    }
+  }
   // ---- schedule of the thread-per-trajectory kernel (rollout_fwd.cuh).  Two ways to deal with the tail of a launch:
   //  * time slices (FIFO of continuation records, breadth-first): right when many trajectories run into the pass budget
   //    -- the bench workload, 24 % of them: 24.5 ms against 27.8 ms; passes per slice = 1/128 of the budget, between 8 and

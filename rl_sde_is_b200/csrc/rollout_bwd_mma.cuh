@@ -217,7 +217,15 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MMA_MIN_BLOCKS(D)) rollout_bwd_
 
   // fp32 window sums (flushed to the fp64 partials every MMA_FLUSH_EVERY micro-steps)
   float wW2[2][4][4];                          // 2^dsh x dW2[out = 16 mt + g + 8 (r >> 1)][in = 8 j + 2 q + (r & 1)]
-  float wb1[4][2], wb2[4][2], wW1[4][2][D], wW3[4][2][D], wb3[D];    // column 8 j + 2 q + e, partial over this thread's rows
+  // column 8 j + 2 q + e, partial over this thread's rows.  The d-sized blocks (16 d floats per thread) live in registers
+  // for d <= 4 and in shared memory above (d = 10: 160 accumulators would spill; one read-modify-write per entry and
+  // half-pass instead)
+  constexpr bool SMEM_ACC = D > 4;
+  constexpr int NREG_ACC = SMEM_ACC ? 1 : D;
+  extern __shared__ float bwdm_smem[];
+  float* const sW1acc = bwdm_smem + threadIdx.x;                      // [(j, e, k)][blockDim.x]
+  float* const sW3acc = bwdm_smem + (size_t)8 * D * blockDim.x + threadIdx.x;
+  float wb1[4][2], wb2[4][2], wW1[4][2][NREG_ACC], wW3[4][2][NREG_ACC], wb3[D];
   int dsh = 0;                                 // the deltas enter the tensor cores as dz2 2^dsh (warp-uniform)
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
@@ -231,7 +239,10 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MMA_MIN_BLOCKS(D)) rollout_bwd_
     for (int e = 0; e < 2; ++e) {
       wb1[j][e] = 0.f; wb2[j][e] = 0.f;
 #pragma unroll
-      for (int k = 0; k < D; ++k) { wW1[j][e][k] = 0.f; wW3[j][e][k] = 0.f; }
+      for (int k = 0; k < D; ++k) {
+        if constexpr (SMEM_ACC) { sW1acc[(size_t)((j * 2 + e) * D + k) * blockDim.x] = 0.f; sW3acc[(size_t)((j * 2 + e) * D + k) * blockDim.x] = 0.f; }
+        else { wW1[j][e][k] = 0.f; wW3[j][e][k] = 0.f; }
+      }
     }
 #pragma unroll
   for (int k = 0; k < D; ++k) wb3[k] = 0.f;
@@ -277,14 +288,20 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MMA_MIN_BLOCKS(D)) rollout_bwd_
         wb1[j][e] = 0.f; wb2[j][e] = 0.f;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-          float a1 = wW1[j][e][k], a3 = wW3[j][e][k];
+          float a1, a3;
+          if constexpr (SMEM_ACC) {
+            a1 = sW1acc[(size_t)((j * 2 + e) * D + k) * blockDim.x]; a3 = sW3acc[(size_t)((j * 2 + e) * D + k) * blockDim.x];
+            sW1acc[(size_t)((j * 2 + e) * D + k) * blockDim.x] = 0.f; sW3acc[(size_t)((j * 2 + e) * D + k) * blockDim.x] = 0.f;
+          } else {
+            a1 = wW1[j][e][k]; a3 = wW3[j][e][k];
+            wW1[j][e][k] = 0.f; wW3[j][e][k] = 0.f;
+          }
 #pragma unroll
           for (int o = 4; o < 32; o <<= 1) { a1 += __shfl_xor_sync(FULL, a1, o); a3 += __shfl_xor_sync(FULL, a3, o); }
           if (g == 0) {
             oW1[col * D + k] = (flushed_once ? oW1[col * D + k] : 0.0) + (double)a1;
             oW3[k * H + col] = (flushed_once ? oW3[k * H + col] : 0.0) + (double)a3;
           }
-          wW1[j][e][k] = 0.f; wW3[j][e][k] = 0.f;
         }
       }
 #pragma unroll
@@ -461,18 +478,22 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MMA_MIN_BLOCKS(D)) rollout_bwd_
 #pragma unroll
           for (int k = 0; k < D; ++k) w3[k] = *reinterpret_cast<const float2*>(&s_W3[k][8 * jj + 2 * q]);
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int h = r >> 1, e = r & 1;
-            const float hv = h2[jj][r];
-            float dh = 0.f;
+          for (int e = 0; e < 2; ++e) {
+            const float hv0 = h2[jj][e], hv1 = h2[jj][2 + e];          // rows g and g + 8
+            float dh0 = 0.f, dh1 = 0.f;
 #pragma unroll
             for (int k = 0; k < D; ++k) {
-              dh = fmaf(ar[h][k], e ? w3[k].y : w3[k].x, dh);
-              wW3[jj][e][k] = fmaf(ar[h][k], hv, wW3[jj][e][k]);
+              const float w = e ? w3[k].y : w3[k].x;
+              dh0 = fmaf(ar[0][k], w, dh0);
+              dh1 = fmaf(ar[1][k], w, dh1);
+              const float v = fmaf(ar[0][k], hv0, ar[1][k] * hv1);
+              if constexpr (SMEM_ACC) sW3acc[(size_t)((jj * 2 + e) * D + k) * blockDim.x] += v;
+              else wW3[jj][e][k] += v;
             }
-            const float dz = dh * fmaf(-hv, hv, 1.0f);
-            wb2[jj][e] += dz;
-            dz2[jj][r] = dz;
+            const float dzA = dh0 * fmaf(-hv0, hv0, 1.0f), dzB = dh1 * fmaf(-hv1, hv1, 1.0f);
+            wb2[jj][e] += dzA + dzB;
+            dz2[jj][e] = dzA;
+            dz2[jj][2 + e] = dzB;
           }
         }
         uint32_t a2h[2][4], a2l[2][4];
@@ -497,15 +518,18 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MMA_MIN_BLOCKS(D)) rollout_bwd_
 #pragma unroll
             for (int k = 0; k < D; ++k) ww[k] = *reinterpret_cast<const float2*>(&s_W1[k][8 * jj + 2 * q]);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              const int h = r >> 1, e = r & 1;
-              const float hv = h1[jj][r];
-              const float dz = dz1[jj][r] * un * fmaf(-hv, hv, 1.0f);
-              wb1[jj][e] += dz;
+            for (int e = 0; e < 2; ++e) {
+              const float hv0 = h1[jj][e], hv1 = h1[jj][2 + e];
+              const float dzA = dz1[jj][e] * un * fmaf(-hv0, hv0, 1.0f), dzB = dz1[jj][2 + e] * un * fmaf(-hv1, hv1, 1.0f);
+              wb1[jj][e] += dzA + dzB;
 #pragma unroll
               for (int k = 0; k < D; ++k) {
-                wW1[jj][e][k] = fmaf(dz, xr[h][k], wW1[jj][e][k]);
-                dxp[h][k] = fmaf(e ? ww[k].y : ww[k].x, dz, dxp[h][k]);
+                const float v = fmaf(dzA, xr[0][k], dzB * xr[1][k]);
+                if constexpr (SMEM_ACC) sW1acc[(size_t)((jj * 2 + e) * D + k) * blockDim.x] += v;
+                else wW1[jj][e][k] += v;
+                const float w = e ? ww[k].y : ww[k].x;
+                dxp[0][k] = fmaf(w, dzA, dxp[0][k]);
+                dxp[1][k] = fmaf(w, dzB, dxp[1][k]);
               }
             }
           }

@@ -19,12 +19,15 @@ static int launch_bwd_mma_variant(const float* params_host, const FwdArgs& args,
   auto kern = rollout_bwd_mma_kernel<D, FAST>;
   int block = 128;
   long long grid;
+  // d > 4: the d-sized gradient blocks accumulate in shared memory, 16 d floats per thread
+  auto dyn_smem = [](int blk) { return D > 4 ? (size_t)16 * D * blk * sizeof(float) : (size_t)0; };
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem(128));
   if (args.K <= (long long)sm_count * 128) {
     block = 32;
     grid = (args.K + 31) / 32;
   } else {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, dyn_smem(block)) != cudaSuccess || per_sm < 1) per_sm = 1;
     grid = (long long)sm_count * per_sm;
     const long long need = (args.K + block - 1) / block;
     if (grid > need) grid = need;
@@ -32,7 +35,7 @@ static int launch_bwd_mma_variant(const float* params_host, const FwdArgs& args,
   if (grid < 1) grid = 1;
   long long n_warps = grid * (block / 32);
   if (n_warps > BWD_MAX_WARPS) { grid = BWD_MAX_WARPS / (block / 32); n_warps = grid * (block / 32); }
-  kern<<<(unsigned)grid, block, 0, stream>>>(W, args, F, reinterpret_cast<double*>(partial));
+  kern<<<(unsigned)grid, block, dyn_smem(block), stream>>>(W, args, F, reinterpret_cast<double*>(partial));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if (join != nullptr && (e = cudaStreamWaitEvent(stream, join, 0)) != cudaSuccess) return (int)e;

@@ -33,17 +33,22 @@
 namespace rlsde {
 
 constexpr int UMMA_M = 128;                 // trajectories per tile = TMEM lanes
-constexpr int UMMA_THREADS = 192;
-constexpr int UMMA_STAGES = 4;                // weight stages (one k-step of B, hi + lo, each)
-constexpr int UMMA_ASLOTS = 4;                // activation slots (one k-step of A, hi + lo, each)
+constexpr int UMMA_STAGES = 4;                // weight stages (one k-step of B, hi + lo, each) when the weights are streamed
 constexpr uint32_t UMMA_ACHUNK = UMMA_M * 16 * 2 * 2;   // bytes of one A slot: 128 rows x 16 halfs, hi + lo
+// Hidden widths up to 64 keep the whole float16 hi / lo image of W2 in shared memory (4 KB at H = 32): no producer warp,
+// 160 threads, four or more CTAs per SM.  Above, the image is streamed every pass (192 threads, two CTAs per SM).
+template <int H> __host__ __device__ constexpr bool umma_streams() { return H > 64; }
+template <int H> __host__ __device__ constexpr int umma_threads() { return umma_streams<H>() ? 192 : 160; }
+template <int H> __host__ __device__ constexpr int umma_aslots() { return H / 16 < 4 ? H / 16 : 4; }   // activation slots (one k-step of A each)
+template <int H> __host__ __device__ constexpr int umma_tmem_cols() { return H < 32 ? 32 : H; }
 
 template <int H> __host__ __device__ constexpr size_t umma_chunk_bytes() { return (size_t)H * 64; }        // hi + lo of one k-step
 template <int H> __host__ __device__ constexpr size_t umma_image_bytes() { return umma_chunk_bytes<H>() * (H / 16); }
 template <int D, int H>
 __host__ __device__ constexpr size_t umma_smem_bytes() {
-  // the A ring, the weight ring, the small layers (W1t [D][H], b1, b2, W3 [D][H])
-  return (size_t)UMMA_ASLOTS * UMMA_ACHUNK + UMMA_STAGES * umma_chunk_bytes<H>() + (size_t)(2 * D + 2) * H * sizeof(float);
+  // the A ring, the weight ring (or the whole image), the small layers (W1t [D][H], b1, b2, W3 [D][H])
+  return (size_t)umma_aslots<H>() * UMMA_ACHUNK + (umma_streams<H>() ? UMMA_STAGES * umma_chunk_bytes<H>() : umma_image_bytes<H>()) +
+         (size_t)(2 * D + 2) * H * sizeof(float);
 }
 
 // host: W2 (pre-scaled like MlpConst / WideParams: w2s[out * H + in]) -> the B-operand image streamed by the kernel.
@@ -120,17 +125,19 @@ __device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }  // namespace umma
 
 template <int D, int H, bool F64, bool FAST>
-__global__ void __launch_bounds__(UMMA_THREADS, 2) rollout_fwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict__ Bimg,
+__global__ void __launch_bounds__(umma_threads<H>(), umma_streams<H>() ? 2 : 4) rollout_fwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict__ Bimg,
                                                                            const __grid_constant__ FwdArgs A) {
   using namespace umma;
   typedef WideParams<D, H> L;
   constexpr int KSTEPS = H / 16;
+  constexpr bool STREAM = umma_streams<H>();
+  constexpr int UMMA_ASLOTS = umma_aslots<H>();
   constexpr uint32_t CHUNK = (uint32_t)umma_chunk_bytes<H>();
   extern __shared__ __align__(128) uint8_t umma_smem[];
   uint8_t* const smem = umma_smem;
   uint8_t* sA = smem;                                           // UMMA_ASLOTS x [hi 4 KB | lo 4 KB]
   uint8_t* sB = smem + UMMA_ASLOTS * UMMA_ACHUNK;
-  float* sW1 = reinterpret_cast<float*>(sB + UMMA_STAGES * CHUNK);     // [D][H]
+  float* sW1 = reinterpret_cast<float*>(sB + (STREAM ? UMMA_STAGES * CHUNK : (uint32_t)umma_image_bytes<H>()));     // [D][H]
   float* sb1 = sW1 + D * H;
   float* sb2 = sb1 + H;
   float* sW3 = sb2 + H;                                                // [D][H]
@@ -140,7 +147,12 @@ __global__ void __launch_bounds__(UMMA_THREADS, 2) rollout_fwd_umma_kernel(const
   const bool inject = (A.flags & RLSDE_F_NOISE_INJECTED) != 0;
   const long long lim = inject ? (A.noise_steps < A.n_steps_lim ? A.noise_steps : A.n_steps_lim) : A.n_steps_lim;
 
-  for (int i = tid; i < H; i += UMMA_THREADS) {
+  if constexpr (!STREAM) {          // resident weights: the whole image, once
+    for (int i = tid; i < (int)(umma_image_bytes<H>() / 16); i += blockDim.x)
+      reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(Bimg) + i);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  for (int i = tid; i < H; i += blockDim.x) {
     sb1[i] = __ldg(Wp + L::o_b1 + i);
     sb2[i] = __ldg(Wp + L::o_b2 + i);
 #pragma unroll
@@ -153,7 +165,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 2) rollout_fwd_umma_kernel(const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(H) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(umma_tmem_cols<H>()) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -264,9 +276,9 @@ __global__ void __launch_bounds__(UMMA_THREADS, 2) rollout_fwd_umma_kernel(const
 #pragma unroll 1
         for (int ks = 0; ks < KSTEPS; ++ks) {
           const unsigned c = pass * KSTEPS + ks;                  // running k-step index
-          const int s = c % UMMA_STAGES, slot = c % UMMA_ASLOTS;
+          const int s = STREAM ? c % UMMA_STAGES : ks, slot = c % UMMA_ASLOTS;
           mbar_wait(&a_full[slot], (c / UMMA_ASLOTS) & 1u);       // (also orders the previous pass's accumulator reads first)
-          mbar_wait(&full[s], (c / UMMA_STAGES) & 1u);
+          if constexpr (STREAM) mbar_wait(&full[s], (c / UMMA_STAGES) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_base = smem_u32(sA) + (uint32_t)slot * UMMA_ACHUNK;
           const uint64_t ah = make_desc(a_base, (UMMA_M / 8) * 128, 128);
@@ -277,11 +289,11 @@ __global__ void __launch_bounds__(UMMA_THREADS, 2) rollout_fwd_umma_kernel(const
           mma_f16(tmem_base, al, bh, idesc, 1u);
           mma_f16(tmem_base, ah, bl, idesc, 1u);
           commit(&a_empty[slot]);                                 // both rings get their slot back once these MMAs have read it
-          commit(&empty[s]);
+          if constexpr (STREAM) commit(&empty[s]);
         }
         commit(&acc_ready);
       }
-    } else {
+    } else if constexpr (STREAM) {
       if (lane == 0) {
 #pragma unroll 1
         for (int ks = 0; ks < KSTEPS; ++ks) {
@@ -295,7 +307,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 2) rollout_fwd_umma_kernel(const
     }
   }
   __syncthreads();
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(H) : "memory");
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(umma_tmem_cols<H>()) : "memory");
 }
 
 // params_dev: WideParams<D, H> image; image_dev: umma_image_bytes<H>() bytes (both in the caller's workspace)

@@ -15,13 +15,20 @@ static int launch_fwd_umma_variant(const float* params_dev, const uint8_t* image
   // back while the other's MMAs run
   // (the occupancy query answers 1 under the default carveout, so the carveout is requested and the count derived here)
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-  int per_sm = (2 * (smem + 2048) <= (size_t)227 * 1024) ? 2 : 1;
-  if (per_sm > 512 / H) per_sm = 512 / H;                      // tensor memory: 512 columns per SM
+  constexpr int THREADS = umma_threads<H>();
+  cudaFuncAttributes fa;
+  if ((e = cudaFuncGetAttributes(&fa, kern)) != cudaSuccess) return (int)e;
+  int per_sm = (int)(((size_t)227 * 1024) / (smem + 2048));
+  const int by_regs = 65536 / (THREADS * (fa.numRegs > 0 ? ((fa.numRegs + 7) & ~7) : 128));
+  if (per_sm > by_regs) per_sm = by_regs;
+  if (per_sm > 512 / umma_tmem_cols<H>()) per_sm = 512 / umma_tmem_cols<H>();     // tensor memory: 512 columns per SM
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
   long long grid = (long long)sm_count * per_sm;
   const long long need = (args.K + UMMA_M - 1) / UMMA_M;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, UMMA_THREADS, smem, stream>>>(params_dev, image_dev, args);
+  kern<<<(unsigned)grid, THREADS, smem, stream>>>(params_dev, image_dev, args);
   note_kernel_launches(1);
   return (int)cudaGetLastError();
 }

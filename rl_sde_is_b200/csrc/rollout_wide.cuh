@@ -24,7 +24,7 @@
 namespace rlsde {
 
 // Device copy of a wide policy (float32, in the caller's workspace):
-//   W1t [D][H], b1 [H], W2t [H][H] (input-major), W2 [H][H] (output-major), b2 [H], W3 [D][H], b3 [4]
+//   W1t [D][H], b1 [H], W2t [H][H] (input-major), W2 [H][H] (output-major), b2 [H], W3 [D][H], b3 [D rounded up to 4]
 // hidden layers pre-scaled by 2 log2(e) for the precise tanh, exactly like MlpConst.
 template <int D, int H>
 struct WideParams {
@@ -35,9 +35,9 @@ struct WideParams {
   static constexpr size_t o_b2 = o_W2 + (size_t)H * H;
   static constexpr size_t o_W3 = o_b2 + H;
   static constexpr size_t o_b3 = o_W3 + (size_t)D * H;
-  static constexpr size_t count = o_b3 + 4;
+  static constexpr size_t count = o_b3 + ((D + 3) & ~3);
 };
-constexpr size_t WIDE_PARAM_BYTES_MAX = (2 * 256 * 256 + 2 * RLSDE_MAX_D * 256 + 2 * 256 + 4) * sizeof(float);
+constexpr size_t WIDE_PARAM_BYTES_MAX = (2 * 256 * 256 + 2 * RLSDE_MAX_D * 256 + 2 * 256 + RLSDE_MAX_D) * sizeof(float);
 
 template <int D, int H>
 inline void pack_wide_params(const float* p, bool fast_tanh, float* out) {
@@ -61,7 +61,7 @@ inline void pack_wide_params(const float* p, bool fast_tanh, float* out) {
   for (int j = 0; j < H; ++j) out[L::o_b2 + j] = (float)(s * (double)b2[j]);
   for (int k = 0; k < D; ++k)
     for (int j = 0; j < H; ++j) out[L::o_W3 + (size_t)k * H + j] = W3[k * H + j];
-  for (int k = 0; k < 4; ++k) out[L::o_b3 + k] = k < D ? b3[k] : 0.0f;
+  for (int k = 0; k < ((D + 3) & ~3); ++k) out[L::o_b3 + k] = k < D ? b3[k] : 0.0f;
 }
 
 constexpr int WIDE_THREADS = 128;

@@ -142,9 +142,9 @@ def rollout_forward(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=10**6, 
         flags |= L.F_STOCH_INT_EXACT
     elif stoch_int != "reference":
         raise L.RlsdeError("stoch_int must be 'reference' or 'exact'")
-    if kernel not in ("auto", "thread", "warp"):
-        raise L.RlsdeError("kernel must be 'auto', 'thread' or 'warp'")
-    flags |= {"auto": 0, "thread": L.F_KERNEL_THREAD, "warp": L.F_KERNEL_WARP}[kernel]
+    if kernel not in ("auto", "thread", "warp", "tensor"):
+        raise L.RlsdeError("kernel must be 'auto', 'thread', 'warp' or 'tensor'")
+    flags |= {"auto": 0, "thread": L.F_KERNEL_THREAD, "warp": L.F_KERNEL_WARP, "tensor": L.F_KERNEL_TENSOR}[kernel]
     real = torch.float64 if state_f64 else torch.float32
     if state_f64:
         flags |= L.F_STATE_F64
@@ -310,7 +310,7 @@ def rollout_loss_and_grad(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=1
         cfg.noise_steps = int(noise.shape[0])
     flags |= {"precise": 0, "fast": L.F_TANH_FAST}[tanh]
     flags |= {"reference": 0, "exact": L.F_STOCH_INT_EXACT}[stoch_int]
-    flags |= {"auto": 0, "thread": L.F_KERNEL_THREAD, "warp": L.F_KERNEL_WARP}[kernel]
+    flags |= {"auto": 0, "thread": L.F_KERNEL_THREAD, "warp": L.F_KERNEL_WARP, "tensor": L.F_KERNEL_TENSOR}[kernel]
     lim_eff = min(cfg.n_steps_lim, cfg.noise_steps) if noise is not None else cfg.n_steps_lim
     cfg.ckpt_every = int(ckpt_every)
     cfg.ckpt_stride = (lim_eff + cfg.ckpt_every - 1) // cfg.ckpt_every

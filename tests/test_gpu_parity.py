@@ -35,7 +35,7 @@ def _model_from(npz, prefix, d):
 
 
 # ------------------------------------------------------------------------------ torch path, injected noise
-KERNELS = ["thread", "warp"]      # throughput kernels (trajectory per thread) / latency kernels (trajectory per warp)
+KERNELS = ["thread", "warp", "tensor"]      # trajectory per thread (CUDA cores) / per warp (latency) / per thread with the hidden layer on tcgen05
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
