@@ -854,6 +854,33 @@ def secondary_measurements(dev):
                                     "train_steps_per_s": u / (f_ms + b_ms) * 1e3, "bwd_steps_per_s": u / b_ms * 1e3,
                                     "fp32_frac_train": u / (f_ms + b_ms) * 1e3 * flop_train(1, 32) / 74.45e12,
                                     "note": "6556 FLOP per useful step (forward + reverse, SURVEY 8d)"}
+        # wide policy (hidden width 256, the reference's reinforce() default): forward test rollout on the tcgen05 kernel
+        # (rollout_umma.cuh) and on the CUDA-core tile kernel, K = 2e5.  Tensor roofline: executed MMA work = 3 products
+        # (float16 hi / lo split) x 2 H^2 FLOP per trajectory-step, against the measured bf16 GEMM peak.
+        H = 256
+        mw = make_policy(1, hidden=H)
+        pw = R2.flat_parameters(mw).detach().numpy()
+        env_w, mlp_w = R2.env_struct(env1, L2.HIT_X0_IN_LB_RB), L2.make_mlp(1, H)
+        wide = {}
+        for name in ("umma", "ffma"):
+            ts = []
+            for it in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ow = R2.rollout_forward(env_w, mlp_w, pw, 200000, seed=it, n_steps_lim=1000, stoch_int="exact", tuning={"wide_kernel": name}, device=dev)
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            uw = float(ow.stats[L2.ST_USEFUL_STEPS])
+            ms = float(min(ts[1:]))
+            wide[name] = {"ms": ms, "steps_per_s": uw / ms * 1e3, "x_fp32_roofline": uw / ms * 1e3 * flop_fwd(1, H) / 74.45e12}
+        exec_tflops = wide["umma"]["steps_per_s"] * 3 * 2 * H * H / 1e12
+        peak_bf16 = float(peaks.get("bf16_tflops", 1599.4))
+        out["wide_policy_h256"] = {"K": 200000, "flop_per_step": flop_fwd(1, H), **wide,
+                                   "tensor_roofline": {"bound": "tensor", "achieved": exec_tflops, "peak": peak_bf16, "unit": "TFLOP/s",
+                                                       "frac": exec_tflops / peak_bf16,
+                                                       "note": "executed tcgen05 work (three f16 MMAs per product) / measured bf16 GEMM peak (MEASURED_PEAKS.json, burst)"},
+                                   "note": "K1u (tcgen05, tensor-memory accumulator, streamed float16 hi/lo weights) against K1x (FFMA tile kernel)"}
     except Exception as exc:
         out["secondary_error"] = repr(exc)
     return out
