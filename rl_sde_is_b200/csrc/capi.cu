@@ -458,9 +458,9 @@ int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
   float* partial_aux = (float*)((char*)partial + bwd_partial_main_bytes());
   // thread-per-trajectory family, hidden width 32: the tensor-core kernel (rollout_bwd_mma.cuh) unless the caller asks for
   // the CUDA-core one (cfg.bwd_kernel == 2; kept for A/B measurements and as a second implementation in the tests)
-  // (state dimensions above 4 stay on the CUDA-core kernel unless asked: there the d-sized blocks of the tensor-core kernel
-  // spill -- d = 10: 39.8 ms against 28.4 ms at K = 2e5, profiles/r02/bwd_mma_variants.log)
-  const bool use_mma = mlp->d_hidden == MMA_H && (cfg->bwd_kernel == 1 || (cfg->bwd_kernel == 0 && env->d <= 4));
+  // (state dimensions above 4: the d-sized products -- layer 1, head, dW1, dW3, dX -- run as padded 16-wide tiles on the
+  // tensor cores as well; d = 10: 16.3 ms against 26.1 ms at K = 2e5, 61 against 109 ms at K = 1e6)
+  const bool use_mma = mlp->d_hidden == MMA_H && cfg->bwd_kernel != 2;
   cudaEvent_t join = nullptr;
   if (n_long > 0) {
     FwdArgs Along = A;

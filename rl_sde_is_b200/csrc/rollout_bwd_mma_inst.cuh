@@ -16,11 +16,13 @@ static int launch_bwd_mma_variant(const float* params_host, const FwdArgs& args,
   pack_mlp_const<D, MMA_H>(params_host, FAST, W);
   BwdMmaWeights F;
   pack_bwd_mma_weights<D>(W, F);
+  typename BwdMmaSmallSel<D>::type FS;
+  pack_bwd_mma_small<D>(W, FAST, FS);
   auto kern = rollout_bwd_mma_kernel<D, FAST>;
   int block = 128;
   long long grid;
-  // d > 4: the d-sized gradient blocks accumulate in shared memory, 16 d floats per thread
-  auto dyn_smem = [](int blk) { return D > 4 ? (size_t)16 * D * blk * sizeof(float) : (size_t)0; };
+  // d > 4: fragment table of the d-sized products + per-warp staging rows; accumulator tiles (rollout_bwd_mma.cuh)
+  auto dyn_smem = [](int blk) { return bwd_mma_dyn_smem(D, blk); };
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem(128));
   if (args.K <= (long long)sm_count * 128) {
     block = 32;
@@ -35,7 +37,7 @@ static int launch_bwd_mma_variant(const float* params_host, const FwdArgs& args,
   if (grid < 1) grid = 1;
   long long n_warps = grid * (block / 32);
   if (n_warps > BWD_MAX_WARPS) { grid = BWD_MAX_WARPS / (block / 32); n_warps = grid * (block / 32); }
-  kern<<<(unsigned)grid, block, dyn_smem(block), stream>>>(W, args, F, reinterpret_cast<double*>(partial));
+  kern<<<(unsigned)grid, block, dyn_smem(block), stream>>>(W, args, F, FS, reinterpret_cast<double*>(partial));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if (join != nullptr && (e = cudaStreamWaitEvent(stream, join, 0)) != cudaSuccess) return (int)e;
