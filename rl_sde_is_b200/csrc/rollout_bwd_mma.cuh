@@ -520,6 +520,8 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MMA_MIN_BLOCKS(D)) rollout_bwd_
   float Gk = 0.f;
   float lam[D];
   float xs[BWD_MAX_SEG][D];
+  constexpr bool CACHE_DB = NoisePlan<D>::BPP > 1;
+  float dbs[CACHE_DB ? BWD_MAX_SEG : 1][D];
   float xck[D];                    // checkpoint of the NEXT round, loaded one round ahead (its latency hides behind a round)
   NoiseCache<D> nc;
   nc.reset();
@@ -556,7 +558,21 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MMA_MIN_BLOCKS(D)) rollout_bwd_
       float x[D], dB[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) x[i] = xs[s][i];
-      nc.get(A, inject, ok, traj, j, dB);
+      if constexpr (CACHE_DB) {
+        // several Philox blocks per pass: the segment's forward sweep keeps its increments for the reverse sweep
+        if (!inject && !phase_a && s < C - 1) {
+#pragma unroll
+          for (int i = 0; i < D; ++i) dB[i] = dbs[s][i];
+        } else {
+          nc.get(A, inject, ok, traj, j, dB);
+          if (phase_a) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) dbs[s][i] = dB[i];
+          }
+        }
+      } else {
+        nc.get(A, inject, ok, traj, j, dB);
+      }
       float u[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) u[i] = 0.f;

@@ -850,10 +850,11 @@ def test_table_quadrature_path_against_exact_cdf_path(alpha, beta, dt, h):
 
 
 # ------------------------------------------------------------------------------ tensor-core reverse pass
-@pytest.mark.parametrize("d,ckpt", [(1, 1), (1, 8), (2, 1), (3, 4), (10, 16)])
-def test_reverse_pass_tensor_core_kernel_matches_cuda_core_kernel(d, ckpt):
+@pytest.mark.parametrize("d,ckpt,K", [(1, 1, 6000), (1, 8, 6000), (2, 1, 6000), (3, 4, 6000), (10, 16, 6000), (10, 4, 40000), (4, 2, 40000)])
+def test_reverse_pass_tensor_core_kernel_matches_cuda_core_kernel(d, ckpt, K):
     """K2m (mma.sync, float16 x 3 operand split, fp64 partials) against K2 (FFMA2) on the same forward rollout: the two are
-    independent implementations of the same recursion, so they agree to the rounding of fp32 sums of ~1e5 cancelling terms."""
+    independent implementations of the same recursion, so they agree to the rounding of fp32 sums of ~1e5 cancelling terms.
+    (d > 4: the d-sized products are padded HMMA tiles as well; K = 40 000 takes the 128-thread launch shape.)"""
     from rl_sde_is_b200 import _lib as L, rollout as R
     from rl_sde_is_b200.models import DeterministicPolicy
     torch.manual_seed(4)
@@ -862,7 +863,6 @@ def test_reverse_pass_tensor_core_kernel_matches_cuda_core_kernel(d, ckpt):
     env = _make_env(d, 1.0, 1.0, 0.005)
     params = R.flat_parameters(m).detach().numpy()
     env_c, mlp_c = R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(d, 32)
-    K = 6000
     fo = R.rollout_forward(env_c, mlp_c, params, K, seed=21, n_steps_lim=4000, store_path=True, ckpt_every=ckpt, want_logw=False,
                            kernel="thread")
     assert int(fo.stats[L.ST_N_UNFINISHED]) == 0
