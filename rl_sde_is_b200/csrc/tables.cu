@@ -81,10 +81,11 @@ __global__ void __launch_bounds__(128) tables_kernel(const double* __restrict__ 
 //                                                                                 form of cosh's three-term recurrence,
 //                                                                                 stable because the small quantity is kept)
 // 8 FP64 operations and one 8-byte store per entry, re-anchored with exact exp() every GL_ANCHOR cells (measured
-// |P - reference formula| <= 5e-15 at config 3; tests hold 1e-13).  One thread owns one (s, a) column of one
-// GL_ANCHOR-row chunk; columns are the flat index s * Na + a, so every lane of every warp is busy and a block stores
-// 1 KB of contiguous bytes per row.
+// |P - reference formula| <= 5e-15 at config 3; tests hold 1e-13).  One thread owns one (s, a) column of one chunk of
+// at most GL_ANCHOR rows of one row class (see the kernel); columns are the flat index s * Na + a, so every lane of every
+// warp is busy and a block stores 1 KB of contiguous bytes per row.
 constexpr int GL_ANCHOR = 64;
+constexpr double GL_SPAN_SD = 21.0;
 
 struct GlConst {
   double inv_sd, dcell, dstep, rho;        // 1/sd, D, ds, exp(-ds^2)
@@ -119,47 +120,55 @@ static GlConst make_gl_const(double grid_step, double sigma, double dt, double h
 }
 
 // Stores.  A row of P has Ns Na entries and Ns Na is odd at config 3 (401 x 601), so consecutive rows start 72 bytes
-// apart modulo 128: a warp storing its 32 columns writes 256 bytes at 8-byte alignment, i.e. two partial 32-byte sectors
-// per store instruction on three rows out of four, and the SM-to-L2 write path -- not HBM -- is what saturates: 5.4 TB/s
-// here, 6.9 TB/s for the same kernel with an artificial Na = 608 (every row sector-aligned), 7.4 TB/s for a plain fill of
-// the tensor (tools/bench_tables_align.py, tools/bench_fill.py).  Three ways around the misalignment were built and
-// measured in round 2, all slower than storing straight from registers (0.143 ms): rows staged in shared memory and
-// stored rotated to sector boundaries (0.211 ms), rows staged and handed to the TMA unit as 1 KB bulk copies (UBLKCP;
-// 0.209 ms -- the staging loop with its two barriers per eight rows alone takes 0.146 ms), and one warp owning 128
-// columns, four per lane, rotated inside the warp with shuffles (0.160 ms; 112 registers).  Kept: the direct store.
+// apart modulo 128.  With one thread per column walking consecutive rows, a warp's 256-byte store sits at 8-byte alignment
+// on three rows out of four: two partial 32-byte sectors per store instruction, and the SM-to-L2 write path -- not HBM --
+// saturates (5.4 TB/s; 6.9 TB/s for the same kernel with an artificial Na = 608 or 600, i.e. rows sector-aligned;
+// tools/bench_tables_align.py).  Staging the rows (shared memory + rotated stores, TMA bulk copies, in-warp shuffles) was
+// measured slower than that (profiles/r02/tables_store_variants.log).  What is used instead: the rows are split into Q
+// residue classes (Q = 4 for an odd row length, 2 for 2 mod 4, 1 for 0 mod 4).  Within one class every row has the SAME
+// misalignment, so a block that owns (128-column tile, class j, chunk) shifts its tile left by that many columns and
+// every store of every warp is 32-byte aligned; the thread then walks rows j, j + Q, j + 2Q, ... and the recurrences
+// simply run with the step Q ds (their constants are formed on the host for that step).
 __global__ void __launch_bounds__(128) tables_gl_kernel(const double* __restrict__ sgrid, long long Ns,
                                                         const double* __restrict__ agrid, long long Na,
                                                         const unsigned char* __restrict__ in_ts, double inv_nts,
                                                         double alpha, double sigma, double dt, double h,
                                                         long long sp_begin, long long sp_end, double* __restrict__ P,
+                                                        int Q, int steps, long long kc_lo,
                                                         const __grid_constant__ GlConst C) {
   const long long stride = Ns * Na;
-  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= stride) return;
+  const int j = (int)(blockIdx.y % (unsigned)Q);                      // row class
+  const long long kc = kc_lo + blockIdx.y / (unsigned)Q;              // chunk of `steps` rows of that class
+  // columns to shift left so that the first lane's address is a multiple of 32 bytes (the same for every row of the class)
+  const unsigned long long rel = (unsigned long long)(((j - sp_begin) % 4 + 4) % 4) * (unsigned long long)(stride & 3);
+  const long long shift = (long long)((((unsigned long long)P >> 3) + rel) & 3ull);
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x - shift;
+  if (c < 0 || c >= stride) return;
+  // anchors sit at absolute rows Q kc steps + j, so a slab holds exactly the entries of the full tensor
+  const long long r0 = (long long)Q * kc * steps + j;
+  if (r0 >= sp_end) return;
+  const long long i_lo = r0 >= sp_begin ? 0 : (sp_begin - r0 + Q - 1) / Q;     // first stored step
+  long long i_hi = (sp_end - r0 + Q - 1) / Q;                                  // one past the last stored step
+  if (i_hi > steps) i_hi = steps;
+  if (i_lo >= i_hi) return;
+  const long long r_first = r0 + i_lo * Q, r_last = r0 + (i_hi - 1) * Q;
+  const long long row_step = (long long)Q * stride;
+  double* out = P + (r_first - sp_begin) * stride + c;                          // P points at row sp_begin
   const long long s = c / Na, a = c - s * Na;
-  // blockIdx.y picks one anchor-aligned chunk of GL_ANCHOR next-states: many equal work items instead of one
-  // long column per thread, so the grid spreads evenly over the SMs
-  const long long chunk_lo = (sp_begin / GL_ANCHOR + blockIdx.y) * GL_ANCHOR;
-  const long long slab_begin = sp_begin;
-  sp_begin = chunk_lo > sp_begin ? chunk_lo : sp_begin;
-  sp_end = chunk_lo + GL_ANCHOR < sp_end ? chunk_lo + GL_ANCHOR : sp_end;
-  if (sp_begin >= sp_end) return;
-  double* out = P + (sp_begin - slab_begin) * stride + c;              // P points at row slab_begin
   if (in_ts[s]) {
-    for (long long sp = sp_begin; sp < sp_end; ++sp, out += stride) __stcs(out, in_ts[sp] ? inv_nts : 0.0);
+    for (long long sp = r_first; sp <= r_last; sp += Q, out += row_step) __stcs(out, in_ts[sp] ? inv_nts : 0.0);
     return;
   }
   const double xs = __ldg(sgrid + s);
   const double act = __ldg(agrid + a);
-  const double x_lo = __ldg(sgrid + chunk_lo);
+  const double x_lo = __ldg(sgrid + r0);
   const double inv_sd = C.inv_sd, rho = C.rho, mua = C.mu_a, mub = C.mu_b;
   const double grad = __dmul_rn(__dmul_rn(__dmul_rn(4.0, alpha), xs), __dsub_rn(__dmul_rn(xs, xs), 1.0));
   const double mu = __dadd_rn(xs, __dmul_rn(__dadd_rn(-grad, __dmul_rn(sigma, act)), dt));
   // tails folded into the first and the last row of the grid (environments.py:97-101): formed up front, added in registers
-  const double tail_lo = sp_begin == 0 ? ndtr((__ldg(sgrid) - h - mu) * inv_sd) : 0.0;
-  const double tail_hi = sp_end == Ns ? 1.0 - ndtr((__ldg(sgrid + Ns - 1) + h - mu) * inv_sd) : 0.0;
-  // anchors sit at absolute multiples of GL_ANCHOR, so a slab holds exactly the entries of the full tensor
-  const double m = fma(x_lo - h - mu, inv_sd, 0.5 * C.dcell);       // midpoint of cell chunk_lo
+  const double tail_lo = r_first == 0 ? ndtr((__ldg(sgrid) - h - mu) * inv_sd) : 0.0;
+  const double tail_hi = r_last == Ns - 1 ? 1.0 - ndtr((__ldg(sgrid + Ns - 1) + h - mu) * inv_sd) : 0.0;
+  const double m = fma(x_lo - h - mu, inv_sd, 0.5 * C.dcell);       // midpoint of cell r0
   double phi = 0.3989422804014327 * exp(-0.5 * m * m);
   double r = exp(-fma(m, C.dstep, C.half_ds2));
   const double ea = exp(m * C.off_a), eb = exp(m * C.off_b);
@@ -168,19 +177,19 @@ __global__ void __launch_bounds__(128) tables_gl_kernel(const double* __restrict
   // first difference: cosh((m + ds) o) - cosh(m o) = 2 sinh((m + ds/2) o) sinh(ds o / 2)
   double da = C.coef_a * ((ea * C.eh_a - ia / C.eh_a) * C.sh_a);
   double db = C.coef_b * ((eb * C.eh_b - ib / C.eh_b) * C.sh_b);
-  for (long long sp = chunk_lo; sp < sp_begin; ++sp) {      // a slab that starts inside a chunk: advance without storing
+  for (long long i = 0; i < i_lo; ++i) {                    // a slab that starts inside a chunk: advance without storing
     phi *= r; r *= rho;
     ya += da; da = fma(mua, ya, da);
     yb += db; db = fma(mub, yb, db);
   }
-  const int n = (int)(sp_end - sp_begin);
+  const int n = (int)(i_hi - i_lo);
 #pragma unroll 8
-  for (int j = 0; j < n; ++j) {
+  for (int i = 0; i < n; ++i) {
     double p = phi * (ya + yb);
-    if (j == 0) p += tail_lo;
-    if (j == n - 1) p += tail_hi;
+    if (i == 0) p += tail_lo;
+    if (i == n - 1) p += tail_hi;
     __stcs(out, p);                         // streaming store: the tensor is written once and is larger than L2
-    out += stride;
+    out += row_step;
     phi *= r; r *= rho;
     ya += da; da = fma(mua, ya, da);
     yb += db; db = fma(mub, yb, db);
@@ -204,12 +213,25 @@ int launch_tables(const double* state_grid, long long Ns, const double* action_g
   (void)lb; (void)rb;
   const double dcell = 2.0 * h_half / (sigma * sqrt(dt));
   if (P && sprime_end > sprime_begin && uniform_grid && grid_step > 0.0 && Ns >= 2 && dcell <= 0.2 ) {
-    const long long n_chunks = (sprime_end - 1) / GL_ANCHOR - sprime_begin / GL_ANCHOR + 1;
+    // row classes (see tables_gl_kernel) and chunks of `steps` rows per class, both defined on the full grid so that a
+    // slab reproduces the full tensor's entries bit for bit
     const long long cols = Ns * Na;
-    dim3 grid((unsigned)((cols + 127) / 128), (unsigned)n_chunks);
+    const int Q = (cols & 3) == 0 ? 1 : ((cols & 1) == 0 ? 2 : 4);
+    const long long rows_per_class = (Ns + Q - 1) / Q;
+    // a chunk spans at most GL_ANCHOR steps and at most GL_SPAN_SD standard deviations: phi at the anchor must not
+    // underflow (|m| < 37) while cells that matter (|m| < 9) are still ahead of it, and the relative error of r grows
+    // with |m ds|
+    const double step_sd = Q * grid_step / (sigma * sqrt(dt));
+    long long steps_cap = (long long)(GL_SPAN_SD / step_sd);
+    steps_cap = steps_cap < 1 ? 1 : (steps_cap > GL_ANCHOR ? GL_ANCHOR : steps_cap);
+    const long long n_chunks_full = (rows_per_class + steps_cap - 1) / steps_cap;
+    const int steps = (int)((rows_per_class + n_chunks_full - 1) / n_chunks_full);
+    const long long kc_lo = (sprime_begin >= Q ? (sprime_begin - (Q - 1)) / Q : 0) / steps;
+    const long long kc_hi = ((sprime_end - 1) / Q) / steps;
+    dim3 grid((unsigned)((cols + 3 + 127) / 128), (unsigned)((kc_hi - kc_lo + 1) * Q));
     tables_gl_kernel<<<grid, 128, 0, stream>>>(state_grid, Ns, action_grid, Na, in_ts, n_ts > 0 ? 1.0 / (double)n_ts : 0.0,
-                                               alpha, sigma, dt, h_half, sprime_begin, sprime_end, P,
-                                               make_gl_const(grid_step, sigma, dt, h_half));
+                                               alpha, sigma, dt, h_half, sprime_begin, sprime_end, P, Q, steps, kc_lo,
+                                               make_gl_const(Q * grid_step, sigma, dt, h_half));
     note_kernel_launches(1);
   } else if (P && sprime_end > sprime_begin) {
     const long long nsp = sprime_end - sprime_begin;
