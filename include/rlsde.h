@@ -162,6 +162,10 @@ int rlsde_supported(int32_t d, int32_t d_hidden, int32_t n_hidden);
 int64_t rlsde_param_count(const rlsde_mlp* mlp);
 /* bytes of scratch the rollout / backward / reduction kernels need for K trajectories */
 size_t rlsde_workspace_bytes(int64_t K);
+/* the same for a workspace that is also handed to rlsde_rollout_bwd with a policy of this shape: at hidden width 128 / 256
+ * the tcgen05 reverse pass keeps its operand-exchange ring and float64 partials there (about 80 MB on a 148-SM device);
+ * with the smaller rlsde_workspace_bytes(K) buffer the call falls back to the CUDA-core tile kernel */
+size_t rlsde_workspace_bytes_bwd(int64_t K, int32_t d, int32_t d_hidden);
 
 /*
  * Forward rollout of K trajectories (one launch for the whole rollout, not one per pass).

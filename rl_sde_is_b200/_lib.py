@@ -36,7 +36,7 @@ ST_N, ST_N_UNFINISHED, ST_SUM_G, ST_SUM_G2, ST_SUM_T, ST_SUM_T2, ST_SUM_S, ST_SU
 # every symbol include/rlsde.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "rlsde_version", "rlsde_strerror", "rlsde_last_cuda_error", "rlsde_device_info", "rlsde_supported",
-    "rlsde_param_count", "rlsde_workspace_bytes", "rlsde_rollout_fwd", "rlsde_rollout_bwd", "rlsde_reduce_stats",
+    "rlsde_param_count", "rlsde_workspace_bytes", "rlsde_workspace_bytes_bwd", "rlsde_rollout_fwd", "rlsde_rollout_bwd", "rlsde_reduce_stats",
     "rlsde_tables", "rlsde_tables_colsum", "rlsde_env_step", "rlsde_noise_fill",
     "rlsde_dp_scratch_bytes", "rlsde_dp_sweep", "rlsde_dp_rowmax", "rlsde_rollout_transitions", "rlsde_launch_count", "rlsde_reinforce_step",
     "rlsde_reinforce_rollout", "rlsde_reinforce_apply",
@@ -97,6 +97,8 @@ def load():
     lib.rlsde_param_count.argtypes = [C.POINTER(RlsdeMlp)]
     lib.rlsde_workspace_bytes.restype = C.c_size_t
     lib.rlsde_workspace_bytes.argtypes = [i64]
+    lib.rlsde_workspace_bytes_bwd.restype = C.c_size_t
+    lib.rlsde_workspace_bytes_bwd.argtypes = [i64, C.c_int32, C.c_int32]
     lib.rlsde_rollout_fwd.argtypes = [C.POINTER(RlsdeEnv), C.POINTER(RlsdeMlp), vp, C.POINTER(RlsdeRolloutCfg),
                                       vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.rlsde_rollout_transitions.argtypes = [C.POINTER(RlsdeEnv), C.POINTER(RlsdeMlp), vp, C.POINTER(RlsdeRolloutCfg),

@@ -14,6 +14,7 @@
 #include "rollout_bwd_mma.cuh"
 #include "rollout_warp.cuh"
 #include "rollout_wide.cuh"
+#include "rollout_umma_bwd.cuh"
 #include "rollout_umma.cuh"
 
 namespace rlsde {
@@ -217,6 +218,25 @@ size_t rlsde_workspace_bytes(int64_t K) {
   long long cap = 1;
   while (cap < k + WS_MAX_LANES) cap <<= 1;             // the ring's capacity is a power of two
   return ws_fixed_bytes() + (size_t)cap * WS_CONT_REC_BYTES;
+}
+
+// Reverse pass of a wide policy on the tensor cores (rollout_umma_bwd.cuh): its exchange ring and float64 partials live
+// behind the fixed part of the workspace, where the forward rollout keeps its continuation records.
+static size_t bwd_umma_scratch(int d, int H, int sm) {
+#define X(D_, H_) if (d == D_ && H == H_) return bwd_umma_scratch_bytes<D_, H_>(sm);
+  RLSDE_UMMA_SHAPES(X)
+#undef X
+  return 0;
+}
+
+size_t rlsde_workspace_bytes_bwd(int64_t K, int32_t d, int32_t d_hidden) {
+  size_t n = rlsde_workspace_bytes(K);
+  int sm = 0;
+  if ((d_hidden == 128 || d_hidden == 256) && device_sm_count(&sm) == RLSDE_OK) {
+    const size_t need = ws_fixed_bytes() + bwd_umma_scratch(d, d_hidden, sm);
+    if (need > n) n = need;
+  }
+  return n;
 }
 
 // transition-stream outputs of a forward rollout (all null = none)
@@ -432,6 +452,23 @@ int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
   int lrc = -1;
   if (shape_is_wide(env->d, mlp->d_hidden)) {
     if (A.ckpt_every != 1) return RLSDE_ERR_UNSUPPORTED;        // the wide reverse kernel reads every state from the path
+    // hidden width 128 / 256 with enough trajectories for 128-row tiles on at least half the SMs: the tcgen05 kernel
+    // (rollout_umma_bwd.cuh), given a workspace from rlsde_workspace_bytes_bwd; cfg.wide_kernel as in the forward rollout
+    const bool umma_shape = mlp->d_hidden == 128 || mlp->d_hidden == 256;
+    const size_t umma_need = umma_shape ? ws_fixed_bytes() + bwd_umma_scratch(env->d, mlp->d_hidden, sm) : 0;
+    if (umma_shape && cfg->wide_kernel == 1 && workspace_bytes < umma_need) return RLSDE_ERR_WORKSPACE;
+    if (umma_shape && workspace_bytes >= umma_need &&
+        (cfg->wide_kernel == 1 || (cfg->wide_kernel == 0 && A.K >= (long long)sm * UMMA_M / 2))) {
+      uint8_t* scratch = (uint8_t*)workspace_dev + ws_fixed_bytes();
+#define X(D_, H_)                                                                                                        \
+  if (env->d == D_ && mlp->d_hidden == H_)                                                                               \
+    lrc = launch_rollout_bwd_umma<D_, H_>(params_host, ws_wide_params(workspace_dev), ws_umma_image(workspace_dev), A,   \
+                                          (float)loss_scale, grad_dev, scratch, workspace_bytes - ws_fixed_bytes(), sm, stream);
+      RLSDE_UMMA_SHAPES(X)
+#undef X
+      if (lrc != 0) return cuda_fail((cudaError_t)lrc, "rollout_bwd (tcgen05) launch");
+      return RLSDE_OK;
+    }
 #define X(D_, H_)                                                                                                       \
   if (env->d == D_ && mlp->d_hidden == H_)                                                                              \
     lrc = launch_rollout_bwd_wide<D_, H_>(params_host, ws_wide_params(workspace_dev), A, (float)loss_scale, grad_dev, partial, \

@@ -1,0 +1,3 @@
+// tcgen05 reverse pass (producer / consumer CTAs, dW2 in tensor memory) for d = 1, hidden width = 128
+#include "rollout_umma_bwd_inst.cuh"
+RLSDE_INSTANTIATE_UMMA_BWD(1, 128)

@@ -64,11 +64,16 @@ def flat_parameters(model):
 _workspaces = {}
 
 
-def _workspace(device, K=0):
+def _workspace(device, K=0, mlp=None):
     """Scratch buffer for the library, one per (device, stream): the work counters inside must not be shared by concurrent
-    launches.  Sized by the largest batch seen (the forward rollout keeps one 24..168-byte record per trajectory there)."""
+    launches.  Sized by the largest batch seen (the forward rollout keeps one 24..168-byte record per trajectory there);
+    with ``mlp`` (a reverse pass will follow) also by what the tcgen05 reverse kernel of that policy shape needs."""
     key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
-    n = int(L.load().rlsde_workspace_bytes(int(K)))
+    lib = L.load()
+    n = int(lib.rlsde_workspace_bytes(int(K)))
+    if mlp is not None:
+        with torch.cuda.device(device):
+            n = max(n, int(lib.rlsde_workspace_bytes_bwd(int(K), int(mlp.d_in), int(mlp.d_hidden))))
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < n:
         ws = torch.empty(n, dtype=torch.uint8, device=device)
@@ -256,7 +261,7 @@ def rollout_backward(env_c, mlp_c, params_host, fwd: RolloutOut, loss_scale, *, 
         raise L.RlsdeError("the forward rollout must be run with store_path=True")
     params_host = np.ascontiguousarray(params_host, dtype=np.float32)
     grad = torch.empty(int(lib.rlsde_param_count(mlp_c)), dtype=torch.float32, device=dev)
-    ws = _workspace(dev)
+    ws = _workspace(dev, 0, mlp_c)
     with torch.cuda.device(dev):
         # longest trajectories first (stable sort => deterministic): balances the lock-step lanes of the reverse pass
         # (the warp-per-trajectory kernels, used for small batches, take trajectories in index order)
@@ -317,7 +322,7 @@ def rollout_loss_and_grad(env_c, mlp_c, params_host, K, *, seed=0, n_steps_lim=1
     cfg.flags = flags
     L.apply_tuning(cfg, tuning)
     path = torch.empty((K, cfg.ckpt_stride, env_c.d), dtype=torch.float32, device=dev)
-    ws = _workspace(dev, K)
+    ws = _workspace(dev, K, mlp_c)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = lib.rlsde_rollout_fwd(env_c, mlp_c, params_host.ctypes.data, cfg, _ptr(noise), 0, _ptr(G), _ptr(S), _ptr(T), 0, 0,
