@@ -31,7 +31,7 @@
 
 namespace rlsde {
 
-constexpr int UB_THREADS = 192;
+constexpr int UB_THREADS = 320;          // producer: 8 owner warps + MMA issuer + weight loader
 #ifndef UB_RING_N
 #define UB_RING_N 4
 #endif
@@ -45,7 +45,7 @@ constexpr int UB_CSTAGES = UB_CSTAGES_N;          // consumer: k-step chunks in 
 #endif
 constexpr int UB_FLUSH = UB_FLUSH_N;           // consumer: passes between drains of the tensor-memory accumulator
 #ifndef UB_PPC_N
-#define UB_PPC_N 4
+#define UB_PPC_N 2
 #endif
 constexpr int UB_PPC = UB_PPC_N;              // producers per consumer
 constexpr int UB_ASLOTS = 4;           // producer: A-operand ring slots
@@ -95,7 +95,7 @@ __device__ __forceinline__ uint4 ld_cg(const void* p) {
   asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void bar_owners() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_owners() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 // v[c], c = 0..31, one value per column held by every lane  ->  returns on lane l the sum over the 32 lanes of v[l]
 __device__ __forceinline__ float lane_transpose_sum(float (&v)[32], int lane) {
 #pragma unroll
@@ -167,8 +167,8 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
       for (int i = 0; i < UB_PPC; ++i) if (c + i * n_cons < n_prod) npp = i + 1;
       // a pass's slot goes back to its producer once all its chunks have landed; that is known for free when the stage
       // of its last chunk comes round again, so the release trails by up to UB_CSTAGES chunks (two passes can be pending)
-      unsigned* pend_ctl[2];
-      unsigned pend_seq[2], pend_last[2];
+      unsigned* pend_ctl[2] = {nullptr, nullptr};
+      unsigned pend_seq[2] = {0, 0}, pend_last[2] = {0, 0};
       int pend_n = 0;
       auto release_landed = [&](bool all) {
         while (pend_n > 0 && (all || pend_last[0] + UB_CSTAGES < cc + 1u)) {
@@ -287,13 +287,18 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
   }
 
   // ============================================================================================= producer
+  // Threads 0-255 are the owners: TWO threads per trajectory (tr = tid & 127 is the row = TMEM lane; warps w and w + 4
+  // reach the same 32 lanes), each taking every other 32-unit chunk of the hidden layers (cb = 2 i + half).  With one
+  // thread per row a scheduler holds a single warp and every MUFU / tensor-memory latency is exposed (measured: 24 us of
+  // owner work per pass); two warps per scheduler overlap them.  Partial head sums and partial dX meet in shared memory.
   uint8_t* sA = umma_smem;                                           // UB_ASLOTS x [hi 4 KB | lo 4 KB]
   uint8_t* sB = sA + UB_ASLOTS * UMMA_ACHUNK;                        // UMMA_STAGES weight chunks
   float* sW1 = reinterpret_cast<float*>(sB + UMMA_STAGES * CHUNK);   // [D][H]
   float* sb1 = sW1 + D * H;
   float* sb2 = sb1 + H;
   float* sW3 = sb2 + H;                                              // [D][H]
-  float* sAcc = sW3 + D * H;                                         // [4 warps][NQ][H]: b1, b2, W1[D], W3[D] column sums
+  float* sAcc = sW3 + D * H;                                         // [4 row groups][NQ][H]: b1, b2, W1[D], W3[D] column sums
+  __shared__ float s_u[2][UMMA_M][D], s_dx[2][UMMA_M][D];
   for (int i = tid; i < H; i += blockDim.x) {
     sb1[i] = __ldg(Wp + L::o_b1 + i);
     sb2[i] = __ldg(Wp + L::o_b2 + i);
@@ -309,7 +314,8 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
   const int p = (int)blockIdx.x;
   unsigned* const pc = ctl + (size_t)p * UB_CTL_WORDS;
   double* const mySmall = partial + (size_t)n_cons * H * H + (size_t)p * ub_small_count<D, H>();
-  const bool owner = warp < 4;
+  const bool owner = warp < 8;
+  const int tr = tid & (UMMA_M - 1), half = (tid >> 7) & 1, rgrp = warp & 3;
   const bool inject = (A.flags & RLSDE_F_NOISE_INJECTED) != 0;
   const bool s_exact = (A.flags & RLSDE_F_STOCH_INT_EXACT) != 0;
   const float inv_s = FAST ? 1.0f : (float)(1.0 / RLSDE_TWO_LOG2E);
@@ -318,32 +324,36 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
   float b3[D];
 #pragma unroll
   for (int k = 0; k < D; ++k) b3[k] = __ldg(Wp + L::o_b3 + k);
-
 #ifdef UB_PROFILE
   long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
 #endif
   unsigned kc = 0;            // running k-step index (A slots and weight stages advance together)
   unsigned pcount = 0;        // running pass index = exchange sequence number
+  const long long n_tiles = (A.K + UMMA_M - 1) / UMMA_M;
 
-  for (long long tile = p; tile * UMMA_M < A.K; tile += n_prod) {
+  // tiles (length-sorted by the caller) are dealt out boustrophedon: round r goes p = 0 .. n_prod-1 when r is even and
+  // back when it is odd, so every producer's total is close to the mean (static, hence deterministic)
+  for (long long rnd = 0; rnd * n_prod < n_tiles; ++rnd) {
+    const long long tile = rnd * n_prod + ((rnd & 1) ? (n_prod - 1 - p) : p);
+    if (tile >= n_tiles) continue;
     // ---- owners pick up their trajectory; the tile runs max (T + 1) passes
     bool alive = false;
     long long traj = 0;
     int kstar = 0, j = -1;
-    float Gk = 0.f, lam[D], gb3[D], xn[D];
+    float Gk = 0.f, lam[D], gb3[D], xn[D], xf[D];
     NoiseCache<D> nc;
     nc.reset();
 #pragma unroll
-    for (int i = 0; i < D; ++i) { lam[i] = 0.f; gb3[i] = 0.f; xn[i] = A.x0_f[i]; }
+    for (int i = 0; i < D; ++i) { lam[i] = 0.f; gb3[i] = 0.f; xn[i] = A.x0_f[i]; xf[i] = A.x0_f[i]; }
     if (owner) {
-      const long long slot = tile * UMMA_M + tid;
+      const long long slot = tile * UMMA_M + tr;
       if (slot < A.K) {
         traj = A.order ? A.order[slot] : slot;
         const int t = A.T[traj];
         if (t >= 0) { alive = true; kstar = t; j = t; Gk = ((const float*)A.G)[traj]; }
       }
       const int np = __reduce_max_sync(0xffffffffu, alive ? j + 1 : 0);
-      if (lane == 0) s_np[warp] = np;
+      if (lane == 0 && half == 0) s_np[rgrp] = np;
       if (alive) {
 #pragma unroll
         for (int i = 0; i < D; ++i) xn[i] = A.path[((long long)traj * A.ckpt_stride + j) * D + i];
@@ -353,9 +363,11 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
     const int n_pass = max(max(s_np[0], s_np[1]), max(s_np[2], s_np[3]));
 
     if (owner) {
-      const uint32_t row_off = (uint32_t)((tid >> 3) * 128 + (tid & 7) * 16);                       // K-major A image (MMA 1, 2)
-      const uint32_t xoff = (uint32_t)(tid >> 4) * XCH + (uint32_t)((tid >> 3) & 1) * 128u + (uint32_t)(tid & 7) * 16u;   // exchange
-      float* const myAcc = sAcc + (size_t)warp * NQ * H;
+      const uint32_t row_off = (uint32_t)((tr >> 3) * 128 + (tr & 7) * 16);                       // K-major A image (MMA 1, 2)
+      const uint32_t xoff = (uint32_t)(tr >> 4) * XCH + (uint32_t)((tr >> 3) & 1) * 128u + (uint32_t)(tr & 7) * 16u;   // exchange
+      const uint32_t tlane = (uint32_t)(32 * rgrp) << 16;
+      float* const myAcc = sAcc + (size_t)rgrp * NQ * H;
+      bool live = false;
 #pragma unroll 1
       for (int ps = 0; ps < n_pass; ++ps, ++pcount, kc += 2 * KSTEPS) {
         const uint32_t par = pcount & 1u;
@@ -366,9 +378,18 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
         }
         bar_owners();
         UB_T(0);
+        // ---- adjoint state after the previous pass (both halves keep a copy; the partial dX are added in a fixed order)
+        if (ps > 0 && live) {
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            const float dxs = (s_dx[0][tr][i] + s_dx[1][tr][i]) * inv_s;
+            const float hess = A.c4a_f[i] * fmaf(3.0f * xf[i], xf[i], -1.0f);
+            lam[i] = fmaf(lam[i], fmaf(-A.dt_f, hess, 1.0f), dxs);
+          }
+          --j;
+        }
         uint8_t* const xs = xbuf + ((size_t)p * UB_RING + (pcount % UB_RING)) * ub_pass_bytes<H>() + xoff;
-        const bool live = alive && j >= 0;
-        float xf[D];
+        live = alive && j >= 0;
 #pragma unroll
         for (int i = 0; i < D; ++i) xf[i] = xn[i];
         if (live && j >= 1) {                      // next pass's state: issued now, used in a pass's time
@@ -376,46 +397,51 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
           for (int i = 0; i < D; ++i) xn[i] = A.path[((long long)traj * A.ckpt_stride + (j - 1)) * D + i];
         }
 
-        // ---- layer 1 -> A ring (K-major, MMA 1) and exchange B planes (MN-major operand of dW2)
+        // ---- layer 1 -> A ring (K-major, MMA 1) and exchange B planes (MN-major operand of dW2); this half's chunks
 #pragma unroll 1
-        for (int ks = 0; ks < KSTEPS; ++ks) {
-          const unsigned c = kc + ks;
-          const int slot = c % UB_ASLOTS;
-          if (c >= UB_ASLOTS) mbar_wait(&a_empty[slot], ((c / UB_ASLOTS) - 1u) & 1u);
-          uint8_t* dst = sA + (size_t)slot * UMMA_ACHUNK + row_off;
+        for (int ci = 0; ci < H / 64; ++ci) {
+          const int cb = 2 * ci + half;
+#pragma unroll 1
+          for (int hs = 0; hs < 2; ++hs) {
+            const int ks = 2 * cb + hs;
+            const unsigned c = kc + ks;
+            const int slot = c % UB_ASLOTS;
+            if (c >= UB_ASLOTS) mbar_wait(&a_empty[slot], ((c / UB_ASLOTS) - 1u) & 1u);
+            uint8_t* dst = sA + (size_t)slot * UMMA_ACHUNK + row_off;
 #pragma unroll
-          for (int kc2 = 0; kc2 < 2; ++kc2) {
-            const int ub = 2 * ks + kc2;
-            float h[8];
+            for (int kc2 = 0; kc2 < 2; ++kc2) {
+              const int ub = 2 * ks + kc2;
+              float h[8];
 #pragma unroll
-            for (int q4 = 0; q4 < 2; ++q4) {
-              const float4 bb = *reinterpret_cast<const float4*>(sb1 + 8 * ub + 4 * q4);
-              float zz[4] = {bb.x, bb.y, bb.z, bb.w};
+              for (int q4 = 0; q4 < 2; ++q4) {
+                const float4 bb = *reinterpret_cast<const float4*>(sb1 + 8 * ub + 4 * q4);
+                float zz[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-              for (int k = 0; k < D; ++k) {
-                const float4 ww = *reinterpret_cast<const float4*>(sW1 + k * H + 8 * ub + 4 * q4);
-                zz[0] = fmaf(xf[k], ww.x, zz[0]); zz[1] = fmaf(xf[k], ww.y, zz[1]);
-                zz[2] = fmaf(xf[k], ww.z, zz[2]); zz[3] = fmaf(xf[k], ww.w, zz[3]);
+                for (int k = 0; k < D; ++k) {
+                  const float4 ww = *reinterpret_cast<const float4*>(sW1 + k * H + 8 * ub + 4 * q4);
+                  zz[0] = fmaf(xf[k], ww.x, zz[0]); zz[1] = fmaf(xf[k], ww.y, zz[1]);
+                  zz[2] = fmaf(xf[k], ww.z, zz[2]); zz[3] = fmaf(xf[k], ww.w, zz[3]);
+                }
+                tanh_pair<FAST>(pack2(zz[0], zz[1]), h[4 * q4], h[4 * q4 + 1]);
+                tanh_pair<FAST>(pack2(zz[2], zz[3]), h[4 * q4 + 2], h[4 * q4 + 3]);
               }
-              tanh_pair<FAST>(pack2(zz[0], zz[1]), h[4 * q4], h[4 * q4 + 1]);
-              tanh_pair<FAST>(pack2(zz[2], zz[3]), h[4 * q4 + 2], h[4 * q4 + 3]);
+              uint4 hi, lo;
+              split_pair(h[0], h[1], hi.x, lo.x);
+              split_pair(h[2], h[3], hi.y, lo.y);
+              split_pair(h[4], h[5], hi.z, lo.z);
+              split_pair(h[6], h[7], hi.w, lo.w);
+              const uint32_t off = (uint32_t)kc2 * (UMMA_M / 8) * 128;
+              *reinterpret_cast<uint4*>(dst + off) = hi;
+              *reinterpret_cast<uint4*>(dst + UMMA_ACHUNK / 2 + off) = lo;
+              *reinterpret_cast<uint4*>(xs + 2 * PLANE + (uint32_t)ub * 256u) = hi;
+              *reinterpret_cast<uint4*>(xs + 3 * PLANE + (uint32_t)ub * 256u) = lo;
             }
-            uint4 hi, lo;
-            split_pair(h[0], h[1], hi.x, lo.x);
-            split_pair(h[2], h[3], hi.y, lo.y);
-            split_pair(h[4], h[5], hi.z, lo.z);
-            split_pair(h[6], h[7], hi.w, lo.w);
-            const uint32_t off = (uint32_t)kc2 * (UMMA_M / 8) * 128;
-            *reinterpret_cast<uint4*>(dst + off) = hi;
-            *reinterpret_cast<uint4*>(dst + UMMA_ACHUNK / 2 + off) = lo;
-            *reinterpret_cast<uint4*>(xs + 2 * PLANE + (uint32_t)ub * 256u) = hi;
-            *reinterpret_cast<uint4*>(xs + 3 * PLANE + (uint32_t)ub * 256u) = lo;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&a_full[slot]);
           }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(&a_full[slot]);
         }
 
-        // ---- sweep 1: h2 = tanh(z2 + b2) parked in the accumulator's columns, head summed
+        // ---- sweep 1: h2 = tanh(z2 + b2) parked in the accumulator's columns, head summed (this half's chunks)
         UB_T(1);
         mbar_wait(&accZ, par);
         UB_T(2);
@@ -424,9 +450,10 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
 #pragma unroll
         for (int k = 0; k < D; ++k) u[k] = 0.f;
 #pragma unroll 1
-        for (int cb = 0; cb < H / 32; ++cb) {
+        for (int ci = 0; ci < H / 64; ++ci) {
+          const int cb = 2 * ci + half;
           uint32_t r[32];
-          const uint32_t ta = tmemZ + ((uint32_t)(32 * warp) << 16) + (uint32_t)(32 * cb);
+          const uint32_t ta = tmemZ + tlane + (uint32_t)(32 * cb);
           ld32(ta, r);
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
@@ -445,8 +472,11 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
           }
           st32(ta, r);
         }
-
+#pragma unroll
+        for (int k = 0; k < D; ++k) s_u[half][tr][k] = u[k];
+        bar_owners();
         UB_T(3);
+
         // ---- a_j (K2's formula; zero for rows that are not on a trajectory this pass)
         float a[D], dB[D];
         nc.get(A, inject, live, traj, j, dB);
@@ -455,17 +485,19 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
           float v = 0.f;
           if (live) {
             const bool incl = s_exact ? (j < kstar) : true;
-            v = (j < kstar ? (u[i] + b3[i]) * A.dt_f : 0.f) - (incl ? Gk * dB[i] : 0.f) + A.sigma_f * A.dt_f * lam[i];
+            const float ui = (s_u[0][tr][i] + s_u[1][tr][i]) + b3[i];
+            v = (j < kstar ? ui * A.dt_f : 0.f) - (incl ? Gk * dB[i] : 0.f) + A.sigma_f * A.dt_f * lam[i];
           }
           a[i] = v;
-          gb3[i] += v;
+          if (half == 0) gb3[i] += v;
         }
 
         // ---- sweep 2: dz2 = (W3^T a)(1 - h2^2) -> A ring (MMA 2) and exchange A planes, scaled by 2^esh; db2, dW3
 #pragma unroll 1
-        for (int cb = 0; cb < H / 32; ++cb) {
+        for (int ci = 0; ci < H / 64; ++ci) {
+          const int cb = 2 * ci + half;
           uint32_t r[32];
-          ld32(tmemZ + ((uint32_t)(32 * warp) << 16) + (uint32_t)(32 * cb), r);
+          ld32(tmemZ + tlane + (uint32_t)(32 * cb), r);
           float dz[32];
 #pragma unroll
           for (int cI = 0; cI < 32; ++cI) {
@@ -476,8 +508,8 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
             dz[cI] = dh * fmaf(-hv, hv, 1.0f);
           }
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int ks = 2 * cb + half;
+          for (int hs = 0; hs < 2; ++hs) {
+            const int ks = 2 * cb + hs;
             const unsigned c = kc + KSTEPS + ks;
             const int slot = c % UB_ASLOTS;
             mbar_wait(&a_empty[slot], ((c / UB_ASLOTS) - 1u) & 1u);
@@ -485,7 +517,7 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
 #pragma unroll
             for (int kc2 = 0; kc2 < 2; ++kc2) {
               const int ub = 2 * ks + kc2;
-              const int o = 16 * half + 8 * kc2;
+              const int o = 16 * hs + 8 * kc2;
               uint4 hi, lo;
               split_pair(dz[o] * dscale, dz[o + 1] * dscale, hi.x, lo.x);
               split_pair(dz[o + 2] * dscale, dz[o + 3] * dscale, hi.y, lo.y);
@@ -513,10 +545,11 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
 
         UB_T(4);
         // ---- publish the pass to the consumer (which reads it with bulk copies: async proxy)
-        asm volatile("fence.proxy.async;" ::: "memory");
-        __threadfence();
+        // (every owner's stores are ordered before the barrier; the publishing thread's fence + release store then covers
+        // them by cumulativity -- the usual "barrier, one thread fences and flags" pattern)
+        asm volatile("fence.proxy.async.global;" ::: "memory");
         bar_owners();
-        if (tid == 0) st_release(pc, pcount + 1);
+        if (tid == 0) { __threadfence(); st_release(pc, pcount + 1); }
 
         // ---- sweep 3: dz1 = dh1 (1 - h1^2) / s, dX = dz1 W1 / s; db1, dW1
         UB_T(5);
@@ -528,9 +561,10 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
         for (int i = 0; i < D; ++i) dx[i] = 0.f;
         const float un = inv_s * dunscale;
 #pragma unroll 1
-        for (int cb = 0; cb < H / 32; ++cb) {
+        for (int ci = 0; ci < H / 64; ++ci) {
+          const int cb = 2 * ci + half;
           uint32_t r[32];
-          ld32(tmemG + ((uint32_t)(32 * warp) << 16) + (uint32_t)(32 * cb), r);
+          ld32(tmemG + tlane + (uint32_t)(32 * cb), r);
           float dz[32];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -560,33 +594,27 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
           myAcc[0 * H + 32 * cb + lane] += lane_transpose_sum(dz, lane);                     // db1
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");     // the next pass's MMAs overwrite both accumulators
-
-        // ---- adjoint state
-        if (live) {
 #pragma unroll
-          for (int i = 0; i < D; ++i) {
-            const float hess = A.c4a_f[i] * fmaf(3.0f * xf[i], xf[i], -1.0f);
-            lam[i] = fmaf(lam[i], fmaf(-A.dt_f, hess, 1.0f), dx[i] * inv_s);
-          }
-          --j;
+        for (int i = 0; i < D; ++i) s_dx[half][tr][i] = dx[i];                // met at the top of the next pass
+      }
+      // ---- tile done: small blocks to the float64 partial (row groups in index order)
+      if (half == 0) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          float v = gb3[i];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) s_b3[rgrp][i] = v;
         }
       }
-      // ---- tile done: small blocks to the float64 partial (warps in index order)
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        float v = gb3[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_b3[warp][i] = v;
-      }
       bar_owners();
-      for (int e = tid; e < NQ * H; e += UMMA_M) {
+      for (int e = tid; e < NQ * H; e += 2 * UMMA_M) {
         const float v = ((sAcc[e] + sAcc[(size_t)NQ * H + e]) + sAcc[(size_t)2 * NQ * H + e]) + sAcc[(size_t)3 * NQ * H + e];
         mySmall[e] += (double)v;
         sAcc[e] = 0.f; sAcc[(size_t)NQ * H + e] = 0.f; sAcc[(size_t)2 * NQ * H + e] = 0.f; sAcc[(size_t)3 * NQ * H + e] = 0.f;
       }
       if (tid < D) mySmall[NQ * H + tid] += (double)(((s_b3[0][tid] + s_b3[1][tid]) + s_b3[2][tid]) + s_b3[3][tid]);
-    } else if (warp == 4) {
+    } else if (warp == 8) {
       if (lane == 0) {
         constexpr uint32_t idesc = make_idesc(UMMA_M, H);
         unsigned kk = kc, pp = pcount;

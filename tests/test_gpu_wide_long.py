@@ -291,3 +291,68 @@ def test_tcgen05_forward_agrees_with_cuda_core_kernel(H):
     # determinism and independence of the launch shape: a shard of the same global batch reproduces its slice bit for bit
     c = R.rollout_forward(env_c, mlp_c, params, 5000, seed=3, n_steps_lim=4000, traj_offset=700, K_global=K, tuning={"wide_kernel": "umma"})
     assert torch.equal(c.T, a.T[700:5700]) and torch.equal(c.G, a.G[700:5700])
+
+
+# ------------------------------------------------------------------------------ tcgen05 reverse pass (rollout_umma_bwd.cuh)
+@pytest.mark.parametrize("d,H,K,opts", [
+    (1, 256, 128 * 3 + 77, {}),                         # partial last tile, several producers, one consumer
+    (1, 128, 128 * 5 + 1, {}),
+    (2, 128, 128 * 2 + 50, {}),
+    (2, 256, 700, {"stoch_int": "exact"}),
+    (1, 256, 900, {"tanh": "fast"}),
+    (1, 256, 40000, {}),                                # more tiles than producers: second-round tiles, float64 drains
+])
+def test_tcgen05_reverse_pass_matches_cuda_core_kernel(d, H, K, opts):
+    """K2u (producer / consumer CTAs, all three H x H products on the tensor cores) against K2x (FFMA tile kernel) on the
+    same forward rollout: two independent implementations of the reverse recursion.  Small blocks agree to fp32 rounding;
+    the H x H block carries the tensor cores' truncating accumulation (measured ~1e-5 of max |g|).  Deterministic."""
+    from rl_sde_is_b200 import _lib as L, rollout as R
+    from rl_sde_is_b200.models import DeterministicPolicy
+    torch.manual_seed(4)
+    m = DeterministicPolicy(d, d, [H, H], nn.Tanh())
+    m.policy[4].bias.data.fill_(1.0 if d == 1 else 3.0)
+    env = _make_env(d, 1.0, 1.0, 0.005)
+    params = R.flat_parameters(m).detach().numpy()
+    env_c, mlp_c = R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(d, H)
+    fwd = R.rollout_forward(env_c, mlp_c, params, K, seed=12, n_steps_lim=600, store_path=True, ckpt_every=1,
+                            tuning={"wide_kernel": "umma"}, **opts)
+    T = fwd.T.cpu().numpy()
+    assert (T >= 0).mean() > 0.5                 # (d = 1: some trajectories run into the pass budget and are skipped by both)
+    grads = {}
+    for name, wk in (("umma", 1), ("ffma", 2), ("umma2", 1)):
+        fwd.cfg.wide_kernel = wk
+        grads[name] = R.rollout_backward(env_c, mlp_c, params, fwd, 1.0 / K).cpu().numpy().astype(np.float64)
+    assert np.isfinite(grads["umma"]).all()
+    assert np.array_equal(grads["umma"], grads["umma2"])
+    o = [0, d * H, d * H + H, d * H + H + H * H, d * H + 2 * H + H * H, 2 * d * H + 2 * H + H * H, 2 * d * H + 2 * H + H * H + d]
+    for blk, (lo, hi) in zip(("W1", "b1", "W2", "b2", "W3", "b3"), zip(o[:-1], o[1:])):
+        x, y = grads["umma"][lo:hi], grads["ffma"][lo:hi]
+        tol = 1e-4 if blk == "W2" else 2e-5
+        assert np.abs(x - y).max() <= tol * max(np.abs(y).max(), 1e-12), (blk, float(np.abs(x - y).max() / np.abs(y).max()))
+
+
+def test_tcgen05_reverse_pass_needs_its_workspace():
+    """rlsde_workspace_bytes_bwd covers the tensor-core reverse kernel's exchange ring; forced onto that kernel with less,
+    the call answers RLSDE_ERR_WORKSPACE instead of writing past the buffer."""
+    from rl_sde_is_b200 import _lib as L, rollout as R
+    from rl_sde_is_b200.models import DeterministicPolicy
+    lib = L.load()
+    torch.manual_seed(4)
+    m = DeterministicPolicy(1, 1, [256, 256], nn.Tanh())
+    m.policy[4].bias.data.fill_(1.0)
+    env = _make_env(1, 1.0, 1.0, 0.005)
+    params = R.flat_parameters(m).detach().numpy()
+    env_c, mlp_c = R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(1, 256)
+    K = 300
+    fwd = R.rollout_forward(env_c, mlp_c, params, K, seed=1, n_steps_lim=3000, store_path=True, ckpt_every=1)
+    full = int(lib.rlsde_workspace_bytes_bwd(K, 1, 256))
+    assert full >= int(lib.rlsde_workspace_bytes(K)) and full >= (100 << 20)          # 98 producers x 4 passes x 256 KB and partials
+    ws = torch.empty(full, dtype=torch.uint8, device="cuda")
+    g = torch.empty(int(lib.rlsde_param_count(mlp_c)), dtype=torch.float32, device="cuda")
+    args = lambda nbytes: (env_c, mlp_c, params.ctypes.data, fwd.cfg, 0, fwd.G.data_ptr(), fwd.T.data_ptr(), fwd.path.data_ptr(), 0,
+                           1.0 / K, g.data_ptr(), ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream)
+    fwd.cfg.wide_kernel = 1
+    assert lib.rlsde_rollout_bwd(*args(full - (96 << 20))) == -5                 # RLSDE_ERR_WORKSPACE
+    L.check(lib.rlsde_rollout_bwd(*args(full)), "rlsde_rollout_bwd")
+    torch.cuda.synchronize()
+    assert torch.isfinite(g).all()
