@@ -889,6 +889,39 @@ def secondary_measurements(dev):
                                                        "frac": exec_tflops / peak_bf16,
                                                        "note": "executed tcgen05 work (three f16 MMAs per product) / measured bf16 GEMM peak (MEASURED_PEAKS.json, burst)"},
                                    "note": "K1u (tcgen05, tensor-memory accumulator, streamed float16 hi/lo weights) against K1x (FFMA tile kernel)"}
+        # the same policy in training: forward with stored states (K1u) + reverse pass on the tensor cores (K2u: producer /
+        # consumer CTAs, rollout_umma_bwd.cuh) against the CUDA-core tile kernel (K2x), K = 6e4, n_steps_lim = 1000
+        Kw = 60000
+        tw = {}
+        fo = None
+        for it in range(2):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            fo = R2.rollout_forward(env_w, mlp_w, pw, Kw, seed=it, n_steps_lim=1000, store_path=True, ckpt_every=1, want_logw=False,
+                                    tuning={"wide_kernel": "umma"}, device=dev)
+            e[1].record()
+            R2.rollout_backward(env_w, mlp_w, pw, fo, 1.0 / Kw, device=dev)
+            e[2].record()
+            torch.cuda.synchronize()
+            tw = {"fwd_ms": e[0].elapsed_time(e[1]), "bwd_umma_ms": e[1].elapsed_time(e[2])}
+        Tw = fo.T
+        uw_tr = float((Tw[Tw >= 0] + 1).sum())            # passes the reverse recursion walks (trajectories that hit)
+        fo.cfg.wide_kernel = 2
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        R2.rollout_backward(env_w, mlp_w, pw, fo, 1.0 / Kw, device=dev)
+        b.record()
+        torch.cuda.synchronize()
+        tw["bwd_ffma_ms"] = a.elapsed_time(b)
+        f_rev = 2 * flop_fwd(1, H)                          # two more H x H products per pass than the forward
+        out["wide_policy_h256_training"] = {
+            "K": Kw, "reverse_steps": uw_tr, **tw,
+            "bwd_umma_steps_per_s": uw_tr / tw["bwd_umma_ms"] * 1e3, "bwd_ffma_steps_per_s": uw_tr / tw["bwd_ffma_ms"] * 1e3,
+            "bwd_umma_x_fp32_roofline": uw_tr / tw["bwd_umma_ms"] * 1e3 * f_rev / 74.45e12,
+            "bwd_ffma_x_fp32_roofline": uw_tr / tw["bwd_ffma_ms"] * 1e3 * f_rev / 74.45e12,
+            "note": "reverse pass credit = 2 x the forward's FLOP per step (dH1 = dZ2 W2 and dW2 += dZ2^T H1; the recomputed "
+                    "forward product is not credited); K2u runs all three on tcgen05 with float16 hi/lo operands"}
+        del fo
     except Exception as exc:
         out["secondary_error"] = repr(exc)
     return out
