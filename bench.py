@@ -502,9 +502,9 @@ def run_config2(args):
     per_gpu = useful / world / (dev_ms * 1e-3)
     roofline = job.fp32_roofline(per_gpu, flop_fwd(1, 32), clocks,
                                  "Timed per launch with CUDA events incl. the statistics reduction; state lives in registers "
-                                 "(results: 16 B per trajectory).", traffic=2.199e9)
-    roofline["traffic_unit"] = ("bytes per launch (dram read + write, ncu --set full, profiles/r01/ncu_rollout_fwd_v2.txt): the "
-                                "continuation records of the time-sliced schedule, 24 B per 8 passes; 86 GB/s")
+                                 "(results: 16 B per trajectory).", traffic=1.852e9)
+    roofline["traffic_unit"] = ("bytes per launch (dram read + write, ncu --set full, profiles/r02/ncu_rollout_fwd_d1_session2.txt): the "
+                                "continuation records of the time-sliced schedule, 24 B per 8 passes; 74 GB/s")
     extra = {"is_mean": summ.get("is_mean"), "is_rel_error": summ.get("is_rel_error"), "mean_return": summ.get("mean_return"),
              "frac_unfinished": summ["n_unfinished"] / max(summ["n"], 1), "useful_steps_per_step": useful / args.steps,
              "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps, "tanh": args.tanh, "f64_state": f64}

@@ -42,13 +42,13 @@ if "umma" in res and "ffma" in res:
     x, y = res["umma"][lo:hi], res["ffma"][lo:hi]
     print(json.dumps({"W2 shrink coefficient (x-y).y/|y|^2": float(((x - y) * y).sum() / (y * y).sum()), "rms_err_over_rms": float(np.sqrt(((x - y) ** 2).mean() / (y * y).mean())),
                       "corr(err, y)": float(np.corrcoef(x - y, y)[0, 1])}))
-if len(res) >= 2:
+if len(res) >= 2 and "ffma" in res:
     lo, hi = d * H + H, d * H + H + H * H
     for k1 in res:
         for k2 in res:
             if k1 < k2:
                 print(json.dumps({"W2 pair": [k1, k2], "err": float(np.abs(res[k1][lo:hi] - res[k2][lo:hi]).max() / np.abs(res[k2][lo:hi]).max())}))
-if len(res) >= 2:
+if "ffma" in res:
     P = {"W1": (0, d * H), "b1": (d * H, d * H + H), "W2": (d * H + H, d * H + H + H * H), "b2": (d * H + H + H * H, d * H + 2 * H + H * H),
          "W3": (d * H + 2 * H + H * H, 2 * d * H + 2 * H + H * H), "b3": (2 * d * H + 2 * H + H * H, 2 * d * H + 2 * H + H * H + d)}
     ok = True
