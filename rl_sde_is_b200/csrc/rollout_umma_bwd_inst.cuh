@@ -48,11 +48,15 @@ static int launch_bwd_umma_variant(const float* params_dev, const uint8_t* img1,
   if (e != cudaSuccess) return (int)e;
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   double* partial = reinterpret_cast<double*>(scratch + S::o_partial);
-  kern<<<(unsigned)(n_prod + n_cons), UB_THREADS, smem, stream>>>(params_dev, img1, scratch + S::o_img2, args,
-                                                                  scratch + S::o_xbuf(n_prod, n_cons),
-                                                                  reinterpret_cast<unsigned*>(scratch + S::o_ctl), partial, n_prod,
-                                                                  n_cons, esh);
-  e = cudaGetLastError();
+  // producers and consumers wait for each other: a cooperative launch makes the runtime guarantee that the whole grid is
+  // resident at once (it fails with cudaErrorCooperativeLaunchTooLarge instead of deadlocking if it cannot be)
+  const uint8_t* img2 = scratch + S::o_img2;
+  uint8_t* xbuf = scratch + S::o_xbuf(n_prod, n_cons);
+  unsigned* ctl = reinterpret_cast<unsigned*>(scratch + S::o_ctl);
+  FwdArgs a = args;
+  void* kargs[] = {(void*)&params_dev, (void*)&img1, (void*)&img2, (void*)&a, (void*)&xbuf, (void*)&ctl, (void*)&partial,
+                   (void*)&n_prod, (void*)&n_cons, (void*)&esh};
+  e = cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)(n_prod + n_cons)), dim3(UB_THREADS), kargs, smem, stream);
   if (e != cudaSuccess) return (int)e;
   ub_reduce_kernel<D, H><<<(P + 127) / 128, 128, 0, stream>>>(partial, n_prod, n_cons, scale, esh, grad, args.grad_accumulate);
 #ifdef UB_PROFILE
