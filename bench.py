@@ -192,7 +192,7 @@ def run_reference_arm(args):
     vals, units, walls = [], 0.0, 0.0
     threads, kind, how, unit, metric, dtype = 1, "reference" if have_ref else "port", "", UNIT, METRIC, "f64 state / f32 policy"
     if c == 2:
-        K = args.ref_trajectories or 20000
+        K = args.ref_trajectories or 100000
         for _ in range(args.warmup):
             cpu_rollout(2000)
         for s in range(args.steps):
@@ -511,7 +511,7 @@ def run_config2(args):
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cpu_rollout(2000)                                 # warm-up (thread pools, allocator)
-        ck = args.ref_trajectories or 20000
+        ck = args.ref_trajectories or 200000           # ~15 s of host work (the spec's 10-30 s sample)
         v, u, w, thr, kind, how = cpu_rollout(ck)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": thr, "kind": kind, "host_cores": os.cpu_count(),
                         "sample": f"{ck} trajectories x n_steps_lim {lim} ({u} useful steps, {w:.1f} s): {how}"}
