@@ -25,8 +25,14 @@ namespace rlsde {
 // one thread just past the last pair.  The s' axis is cut into n_split chunks (blockIdx.y) so that the grid fills
 // the resident block slots of the GPU almost exactly (see pick_split): equal-sized items, no ragged last wave.
 // Each thread keeps SWEEP_ROWS rows (16 B each) in flight.
-constexpr int SWEEP_ROWS = 8;           // rows per unrolled step (even)
-constexpr int SWEEP_THREADS = 128;
+#ifndef SWEEP_ROWS_N
+#define SWEEP_ROWS_N 4
+#endif
+#ifndef SWEEP_THREADS_N
+#define SWEEP_THREADS_N 128
+#endif
+constexpr int SWEEP_ROWS = SWEEP_ROWS_N;           // rows per unrolled step (even)
+constexpr int SWEEP_THREADS = SWEEP_THREADS_N;
 constexpr int SWEEP_SPLIT_MAX = 16;
 
 __device__ __forceinline__ double2 ld_stream2(const double* p) {
