@@ -61,6 +61,11 @@ __device__ __forceinline__ float mufu_cos(float x) { float y; asm("cos.approx.ft
 // 2 log2(e): hidden-layer weights and biases are pre-multiplied by this on the host for the
 // precise tanh, so that tanh(z) = 1 - 2 / (2^(z') + 1) with z' the accumulated pre-activation.
 #define RLSDE_TWO_LOG2E 2.8853900817779268
+// forward-only thread-per-trajectory kernel: hidden layers pass r = 1 / (exp(2 z) + 1) on, the "1 - 2 r" of the tanh is
+// folded into the next layer's weights (see rsig_pair); 0 = evaluate tanh itself, as the reverse-pass kernels do
+#ifndef RLSDE_FWD_FOLDED
+#define RLSDE_FWD_FOLDED 1
+#endif
 
 // tanh of a packed pair of (pre-scaled) pre-activations.  One asm block per pair: keeping the
 // statement count of the fully unrolled step body low matters for compile time with -lineinfo.
@@ -80,6 +85,18 @@ __device__ __forceinline__ void tanh_pair(u64 acc, float& t0, float& t1) {
         "mov.b64 q, {r0, r1};\n\tfma.rn.f32x2 q, q, %4, %3;\n\tmov.b64 {%0, %1}, q;\n\t}"
         : "=f"(t0), "=f"(t1) : "l"(acc), "l"(0x3f8000003f800000ull), "l"(0xc0000000c0000000ull));
   }
+}
+
+// r = 1 / (2^a + 1) of a packed pair of pre-scaled pre-activations: the precise tanh without its last step,
+// tanh = 1 - 2 r.  The forward-only kernel feeds r to the next layer, whose weights carry the -2 and whose bias carries
+// the row sums (pack_mlp_const_folded): one FFMA2 per pair less on the pipe that bounds that kernel.
+__device__ __forceinline__ void rsig_pair(u64 acc, float& r0, float& r1) {
+  asm("{\n\t.reg .f32 a0, a1, e0, e1, d0, d1;\n\t.reg .b64 p;\n\t"
+      "mov.b64 {a0, a1}, %2;\n\t"
+      "ex2.approx.ftz.f32 e0, a0;\n\tex2.approx.ftz.f32 e1, a1;\n\t"
+      "mov.b64 p, {e0, e1};\n\tadd.rn.f32x2 p, p, %3;\n\tmov.b64 {d0, d1}, p;\n\t"
+      "rcp.approx.ftz.f32 %0, d0;\n\trcp.approx.ftz.f32 %1, d1;\n\t}"
+      : "=f"(r0), "=f"(r1) : "l"(acc), "l"(0x3f8000003f800000ull));
 }
 
 // acc[o .. o+7] (8 packed accumulators = 16 outputs) += h * w[2o .. 2o+15]
@@ -194,6 +211,28 @@ inline void pack_mlp_const(const float* p, bool fast_tanh, MlpConst<D, H>& out) 
   for (int k = 0; k < ((D + 3) & ~3); ++k) out.b3[k] = (k < D) ? b3[k] : 0.0f;
 }
 
+// The same for the forward-only kernel with the precise tanh: hidden layers hand r = (1 - tanh) / 2 to the next layer, so
+//   z2 = b2 + W2 h1 = (b2 + W2 1) + (-2 W2) r1,     u = b3 + W3 h2 = (b3 + W3 1) + (-2 W3) r2
+// -- the factor is a power of two (exact), the folded biases are formed in double and rounded once.
+template <int D, int H>
+inline void pack_mlp_const_folded(const float* p, MlpConst<D, H>& out) {
+  pack_mlp_const<D, H>(p, false, out);
+  const float* W2 = p + H * D + H;  // (H, H)
+  const float* b2 = W2 + H * H;
+  const float* W3 = b2 + H;         // (D, H)
+  const float* b3 = W3 + D * H;
+  for (int j = 0; j < H; ++j) {
+    double rs = 0.0;
+    for (int i = 0; i < H; ++i) { rs += (double)W2[j * H + i]; out.W2t[i][j] = -2.0f * out.W2t[i][j]; }
+    out.b2[j] = (float)(RLSDE_TWO_LOG2E * ((double)b2[j] + rs));
+  }
+  for (int k = 0; k < D; ++k) {
+    double rs = 0.0;
+    for (int j = 0; j < H; ++j) { rs += (double)W3[k * H + j]; out.W3[k][j] = -2.0f * W3[k * H + j]; }
+    out.b3[k] = (float)((double)b3[k] + rs);
+  }
+}
+
 // One row of constant-bank weights into a local array through explicit 16-byte loads.  (SASS is the
 // same LDCU.128 either way; with scalar loads the front end's compile time grows quadratically in
 // the number of constant loads of the fully unrolled kernels.)
@@ -208,7 +247,7 @@ __device__ __forceinline__ void load_row(const float (&src)[N], float (&w)[N]) {
 }
 
 // hidden activations of one layer: hout = tanh(bias + Wt^T hin)   (IN inputs, H outputs)
-template <int IN, int H, bool FAST>
+template <int IN, int H, bool FAST, bool RSIG = false>
 __device__ __forceinline__ void dense_tanh(const float (&Wt)[IN][H], const float (&b)[H], const float (&hin)[IN],
                                            float (&hout)[H]) {
   // Outputs are produced in slabs of 16 (8 packed accumulators): the MUFU work (tanh) of one slab is
@@ -238,7 +277,10 @@ __device__ __forceinline__ void dense_tanh(const float (&Wt)[IN][H], const float
       for (int o = 0; o < SLAB / 2; o += 8) RLSDE_FMA2X8(acc, o, hin[i], w);
     }
 #pragma unroll
-    for (int j = 0; j < SLAB / 2; ++j) tanh_pair<FAST>(acc[j], hout[s0 + 2 * j], hout[s0 + 2 * j + 1]);
+    for (int j = 0; j < SLAB / 2; ++j) {
+      if constexpr (RSIG) rsig_pair(acc[j], hout[s0 + 2 * j], hout[s0 + 2 * j + 1]);
+      else tanh_pair<FAST>(acc[j], hout[s0 + 2 * j], hout[s0 + 2 * j + 1]);
+    }
   }
 }
 
@@ -272,6 +314,37 @@ template <int D, int H, bool FAST>
 __device__ __forceinline__ void mlp_forward(const MlpConst<D, H>& W, const float (&x)[D], float (&u)[D]) {
   float h1[H], h2[H];
   mlp_forward_keep<D, H, FAST>(W, x, h1, h2, u);
+}
+
+// the head of mlp_forward_keep on its own
+template <int D, int H>
+__device__ __forceinline__ void mlp_head(const MlpConst<D, H>& W, const float (&h2)[H], float (&u)[D]) {
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    u64 acc = pack2(W.b3[k], 0.0f);
+    float w[H];
+    load_row<H>(W.W3[k], w);
+#pragma unroll
+    for (int o = 0; o < H; o += 16) {
+      RLSDE_DOT2X6(acc, o, h2, w);
+      u64 a = pack2(h2[o + 12], h2[o + 13]), b = pack2(w[o + 12], w[o + 13]);
+      fma2(acc, a, b);
+      a = pack2(h2[o + 14], h2[o + 15]); b = pack2(w[o + 14], w[o + 15]);
+      fma2(acc, a, b);
+    }
+    float lo, hi;
+    unpack2(acc, lo, hi);
+    u[k] = lo + hi;
+  }
+}
+
+// a = policy(x) from a pack_mlp_const_folded image (precise tanh, forward only)
+template <int D, int H>
+__device__ __forceinline__ void mlp_forward_folded(const MlpConst<D, H>& W, const float (&x)[D], float (&u)[D]) {
+  float r1[H], r2[H];
+  dense_tanh<D, H, false, true>(W.W1t, W.b1, x, r1);
+  dense_tanh<H, H, false, true>(W.W2t, W.b2, r1, r2);
+  mlp_head<D, H>(W, r2, u);
 }
 
 }  // namespace rlsde

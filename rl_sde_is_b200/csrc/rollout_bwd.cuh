@@ -236,7 +236,8 @@ __global__ void __launch_bounds__(128, RLSDE_BWD_MIN_BLOCKS(D)) rollout_bwd_kern
         }
         nc.get(A, inject, ok, traj, j, dB);
         if (phase_a) {
-          // X_{j+1} from X_j: same arithmetic as K1, so the recomputed states are the forward pass's states
+          // X_{j+1} from X_j with K1's environment arithmetic; the policy is K1's up to the rounding of its folded tanh
+          // (RLSDE_FWD_FOLDED), so the recomputed states are the forward pass's states to ~1 ulp per pass
           if (alive && s + 1 < seg_len) em_step_f32<D>(A, x, u, dB);
 #pragma unroll
           for (int i = 0; i < D; ++i) xs[s + 1][i] = x[i];

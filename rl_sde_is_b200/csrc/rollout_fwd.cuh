@@ -333,7 +333,8 @@ __global__ void __launch_bounds__(128, (D == 1 ? 8 : (D <= 4 ? 5 : 4))) rollout_
     float xf[D], u[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) xf[i] = (float)x[i];
-    mlp_forward<D, H, FAST>(W, xf, u);
+    if constexpr (!FAST && RLSDE_FWD_FOLDED) mlp_forward_folded<D, H>(W, xf, u);      // W is a pack_mlp_const_folded image
+    else mlp_forward<D, H, FAST>(W, xf, u);
 
     // ---- this pass's Brownian increments
     float dB[D];

@@ -7,7 +7,8 @@ namespace rlsde {
 template <int D, int H, bool F64, bool FAST>
 static int launch_fwd_variant(const float* params_host, const FwdArgs& args, int sm_count, cudaStream_t stream) {
   MlpConst<D, H> W;
-  pack_mlp_const<D, H>(params_host, FAST, W);
+  if (!FAST && RLSDE_FWD_FOLDED) pack_mlp_const_folded<D, H>(params_host, W);
+  else pack_mlp_const<D, H>(params_host, FAST, W);
   auto kern = rollout_fwd_kernel<D, H, F64, FAST>;
   // Small batches: one warp per block so the warps spread over SMs (latency-bound regime);
   // large batches: persistent grid of 128-thread blocks, as many as are co-resident.

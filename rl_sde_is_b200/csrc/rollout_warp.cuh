@@ -118,6 +118,13 @@ __device__ __forceinline__ void warp_policy(const LaneParams<D>& P, float* slot,
 // in index order, the head as two chains over the even / odd activations added at the end.  ~70 cycles slower per pass
 // than warp_policy, but bit-identical to the thread-per-trajectory kernel, so a trajectory that K1 hands over (the last
 // long trajectories of a launch) continues exactly as K1 would have continued it.
+// (With RLSDE_FWD_FOLDED, K1 hands r = 1 / (exp(2 z) + 1) from layer to layer and its weight image carries the rest of the
+// tanh: P and W are then loaded from a pack_mlp_const_folded image and the activation here stops at r as well.)
+template <bool FAST>
+__device__ __forceinline__ float act_like_k1(float zp) {
+  if constexpr (!FAST && RLSDE_FWD_FOLDED) return mufu_rcp(mufu_ex2(zp) + 1.0f);
+  return tanh_scalar<FAST>(zp);
+}
 template <int D, bool FAST>
 __device__ __forceinline__ void warp_policy_exact(const LaneParams<D>& P, const MlpConst<D, WARP_H>& W, float* slot, int lane,
                                                   const float (&x)[D], float (&u)[D]) {
@@ -125,11 +132,11 @@ __device__ __forceinline__ void warp_policy_exact(const LaneParams<D>& P, const 
 #pragma unroll
   for (int i = 0; i < D; ++i) z = fmaf(x[i], P.w1[i], z);
   float all[WARP_H];
-  warp_allgather(slot, lane, tanh_scalar<FAST>(z), all);
+  warp_allgather(slot, lane, act_like_k1<FAST>(z), all);
   float a = P.b2;
 #pragma unroll
   for (int i = 0; i < WARP_H; ++i) a = fmaf(all[i], P.w2row[i], a);
-  warp_allgather(slot, lane, tanh_scalar<FAST>(a), all);
+  warp_allgather(slot, lane, act_like_k1<FAST>(a), all);
 #pragma unroll
   for (int k = 0; k < D; ++k) {
     float lo = W.b3[k], hi = 0.0f;

@@ -64,7 +64,8 @@ int launch_rollout_fwd_warp(const float* params_host, const void* W_dev, const F
 template <int D, bool F64, bool FAST>
 static int launch_fwd_warp_resume_variant(const float* params_host, const FwdArgs& args, int sm_count, cudaStream_t stream) {
   MlpConst<D, WARP_H> W;
-  pack_mlp_const<D, WARP_H>(params_host, FAST, W);
+  if (!FAST && RLSDE_FWD_FOLDED) pack_mlp_const_folded<D, WARP_H>(params_host, W);      // the image K1 itself was launched with
+  else pack_mlp_const<D, WARP_H>(params_host, FAST, W);
   // the number of records is only known on the device: a full grid (16 warps per SM), warps without a record leave at once
   rollout_fwd_warp_kernel<D, F64, FAST, true><<<(unsigned)(sm_count * 4), 128, 0, stream>>>(W, nullptr, args);
   note_kernel_launches(1);
