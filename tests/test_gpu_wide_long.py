@@ -116,6 +116,29 @@ def test_reinforce_runs_with_the_reference_defaults(tmp_path):
     assert data["exp_time_steps"][-3:].mean() < 0.6 * data["exp_time_steps"][0]
 
 
+def test_reinforce_large_batch_wide_policy_takes_the_tensor_core_kernels(tmp_path):
+    """reinforce() at the reference's default width with a batch large enough for the tcgen05 kernels (forward K1u, reverse
+    K2u through the fused loss-and-gradient call): trains, and the first iteration's loss equals the CUDA-core kernels'."""
+    from rl_sde_is_b200 import _lib as L, utils_path as up
+    from rl_sde_is_b200.reinforce_deterministic_core import reinforce
+    up.set_data_dir(str(tmp_path))
+    env = _make_env(1, 1.0, 1.0, 0.005)
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    K = 64 * n_sm + 500                                      # >= 64 x SMs: automatic dispatch picks the tensor-core kernels
+    before = L.load().rlsde_launch_count()
+    data = reinforce(env, batch_size=K, lr=1e-2, n_iterations=4, seed=1, verbose=False, save=False, n_steps_lim=20000)
+    assert data["d_hidden_layer"] == 256 and np.isfinite(data["losses"]).all()
+    assert data["exp_time_steps"][-1] < 0.9 * data["exp_time_steps"][0]
+    assert L.load().rlsde_launch_count() > before
+    import os
+    os.environ["RLSDE_WIDE_KERNEL"] = "ffma"
+    try:
+        ref = reinforce(env, batch_size=K, lr=1e-2, n_iterations=1, seed=1, verbose=False, save=False, n_steps_lim=20000)
+    finally:
+        del os.environ["RLSDE_WIDE_KERNEL"]
+    np.testing.assert_allclose(data["losses"][0], ref["losses"][0], rtol=2e-4)
+
+
 # ------------------------------------------------------------------------------ long / large replays (noise from the seed)
 @pytest.mark.parametrize("kernel", ["thread", "warp"])
 def test_batch_of_256_with_multi_thousand_pass_paths(golden, kernel):
