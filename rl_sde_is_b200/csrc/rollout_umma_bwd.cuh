@@ -12,8 +12,8 @@
 //   * PRODUCER CTAs (about four fifths of the SMs) run the recursion.  Threads 0-127 own one trajectory each (= one TMEM
 //     lane), exactly as in K1u: layer 1 into the A-operand ring (float16 hi / lo), accumulator read back row by row.
 //     Sweep 1 reads Z2, applies bias + tanh, sums the head and parks h2 in the same tensor-memory columns; the owner then
-//     forms its a_j (K2's formula) and sweep 2 turns h2 into dz2 = (W3^T a)(1 - h2^2), which goes -- scaled by a static
-//     power of two 2^esh so that float16 holds it, hi / lo -- into the A ring again for the second product; sweep 3 reads
+//     forms its a_j (K2's formula) and sweep 2 turns h2 into dz2 = (W3^T a)(1 - h2^2), which goes -- scaled by a power of
+//     two 2^esh chosen per launch from max |G| (ub_scale_kernel) so that float16 holds it, hi / lo -- into the A ring again; sweep 3 reads
 //     dH1, forms dz1 and dX and updates the adjoint.  Warp 4 issues the MMAs, warp 5 streams both weight images
 //     (W2 as [out][in] and as [in][out]) through the mbarrier ring, as in K1u.
 //     The small gradient blocks (b1, W1, b2, W3) are column sums over trajectories: 32-lane butterfly reductions of each
@@ -63,7 +63,7 @@ __host__ __device__ constexpr size_t ub_smem_bytes() {
   return m > (size_t)116 * 1024 ? m : (size_t)116 * 1024;          // more than half an SM: one CTA per SM
 }
 // control words per producer (global, zeroed by the launcher): [0] passes published, [1] passes consumed, [2] finished
-constexpr int UB_CTL_WORDS = 16;        // ([4..11]: cycle counters of the UB_PROFILE build)
+constexpr int UB_CTL_WORDS = 16;        // ([4..11]: cycle counters of the UB_PROFILE build; [12]: esh, the launch's scale exponent)
 
 #ifdef UB_PROFILE
 #define UB_T(i) do { if (tid == 0) { const long long t_ = clock64(); prof[i] += t_ - tprev; tprev = t_; } } while (0)
@@ -117,7 +117,7 @@ template <int D, int H, bool FAST>
 __global__ void __launch_bounds__(UB_THREADS, 1)
 rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict__ Bimg1, const uint8_t* __restrict__ Bimg2,
                         const __grid_constant__ FwdArgs A, uint8_t* __restrict__ xbuf, unsigned* __restrict__ ctl,
-                        double* __restrict__ partial, int n_prod, int n_cons, int esh) {
+                        double* __restrict__ partial, int n_prod, int n_cons) {
   using namespace umma;
   typedef WideParams<D, H> L;
   constexpr int KSTEPS = H / 16;
@@ -319,6 +319,7 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
   const bool inject = (A.flags & RLSDE_F_NOISE_INJECTED) != 0;
   const bool s_exact = (A.flags & RLSDE_F_STOCH_INT_EXACT) != 0;
   const float inv_s = FAST ? 1.0f : (float)(1.0 / RLSDE_TWO_LOG2E);
+  const int esh = (int)pc[12];                                                // set by ub_scale_kernel for this launch
   const float dscale = __uint_as_float((unsigned)(127 + esh) << 23);          // 2^esh
   const float dunscale = __uint_as_float((unsigned)(127 - esh) << 23);
   float b3[D];
@@ -678,10 +679,37 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
   if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
 }
 
+// The launch's scale exponent: dz2 enters the tensor cores as float16 hi / lo of dz2 2^esh.  |dz2| <= |a|_1 max |W3| and
+// a_j = u_j dt - G dB_j + sigma dt lambda_j is dominated by G dB: |a|_1 <~ D (max |G| 8 sqrt(dt) + 1).  esh leaves three binades
+// of head-room above that bound (float16 tops out at 2^16; below it the hi / lo pair keeps an absolute 2^-25, so head-room
+// costs nothing until ~20 binades).  One block; written to word 12 of every producer's control record.
+static __global__ void ub_scale_kernel(const float* __restrict__ G, const int* __restrict__ T, long long K, float w3max, float sqrt_dt,
+                                       int D, int n_prod, unsigned* __restrict__ ctl) {
+  __shared__ float s_max[32];
+  float m = 0.f;
+  for (long long i = threadIdx.x; i < K; i += blockDim.x) if (T[i] >= 0) m = fmaxf(m, fabsf(G[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? s_max[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float bound = w3max * (float)D * (m * 8.0f * sqrt_dt + 1.0f);
+    int e = 0;
+    if (bound > 0.f && isfinite(bound)) frexpf(bound, &e);          // bound < 2^e
+    int esh = 15 - 3 - e;
+    esh = esh > 60 ? 60 : (esh < -60 ? -60 : esh);
+    for (int p = threadIdx.x; p < n_prod; p += 32) ctl[(size_t)p * UB_CTL_WORDS + 12] = (unsigned)esh;
+  }
+}
+
 // grad[...] (+)= scale * (partials in index order); the H x H block carries the 2^-esh unscale
 template <int D, int H>
-static __global__ void ub_reduce_kernel(const double* __restrict__ partial, int n_prod, int n_cons, float scale, int esh,
-                                        float* __restrict__ grad, int accumulate) {
+static __global__ void ub_reduce_kernel(const double* __restrict__ partial, int n_prod, int n_cons, float scale,
+                                        const unsigned* __restrict__ ctl, float* __restrict__ grad, int accumulate) {
+  const int esh = (int)ctl[12];
   constexpr int NQ = ub_nq<D>();
   constexpr int P = D * H + H + H * H + H + H * D + D;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;

@@ -39,7 +39,7 @@ size_t bwd_umma_scratch_bytes(int sm_count) {
 
 template <int D, int H, bool FAST>
 static int launch_bwd_umma_variant(const float* params_dev, const uint8_t* img1, const FwdArgs& args, float scale, float* grad,
-                                   uint8_t* scratch, int n_prod, int n_cons, int esh, cudaStream_t stream) {
+                                   uint8_t* scratch, int n_prod, int n_cons, float w3max, cudaStream_t stream) {
   typedef UbScratch<D, H> S;
   constexpr int P = D * H + H + H * H + H + H * D + D;
   auto kern = rollout_bwd_umma_kernel<D, H, FAST>;
@@ -55,10 +55,11 @@ static int launch_bwd_umma_variant(const float* params_dev, const uint8_t* img1,
   unsigned* ctl = reinterpret_cast<unsigned*>(scratch + S::o_ctl);
   FwdArgs a = args;
   void* kargs[] = {(void*)&params_dev, (void*)&img1, (void*)&img2, (void*)&a, (void*)&xbuf, (void*)&ctl, (void*)&partial,
-                   (void*)&n_prod, (void*)&n_cons, (void*)&esh};
+                   (void*)&n_prod, (void*)&n_cons};
+  ub_scale_kernel<<<1, 1024, 0, stream>>>((const float*)args.G, args.T, args.K, w3max, sqrtf(args.dt_f), D, n_prod, ctl);
   e = cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)(n_prod + n_cons)), dim3(UB_THREADS), kargs, smem, stream);
   if (e != cudaSuccess) return (int)e;
-  ub_reduce_kernel<D, H><<<(P + 127) / 128, 128, 0, stream>>>(partial, n_prod, n_cons, scale, esh, grad, args.grad_accumulate);
+  ub_reduce_kernel<D, H><<<(P + 127) / 128, 128, 0, stream>>>(partial, n_prod, n_cons, scale, ctl, grad, args.grad_accumulate);
 #ifdef UB_PROFILE
   {
     std::vector<unsigned> h((size_t)n_prod * UB_CTL_WORDS);
@@ -72,7 +73,7 @@ static int launch_bwd_umma_variant(const float* params_dev, const uint8_t* img1,
     }
   }
 #endif
-  note_kernel_launches(2);
+  note_kernel_launches(3);
   return (int)cudaGetLastError();
 }
 
@@ -90,28 +91,18 @@ int launch_rollout_bwd_umma(const float* params_host, float* params_dev, uint8_t
   std::vector<uint16_t> w1(umma_image_bytes<H>() / 2), w2(umma_image_bytes<H>() / 2);
   pack_umma_weights<H>(img.data() + WideParams<D, H>::o_W2, w1.data());      // B[n = out][k = in]   (Z2 = H1 W2^T)
   pack_umma_weights<H>(img.data() + WideParams<D, H>::o_W2t, w2.data());     // B[n = in][k = out]   (dH1 = dZ2 W2)
-  // dz2 enters the tensor cores as dz2 2^esh: |dz2| <= sum_i |a_i| max_unit sum_i |W3[i][unit]|; room for |a|_1 up to 2^8
+  // largest head weight: the device picks the launch's scale exponent from it and from max |G| (ub_scale_kernel)
   double w3max = 0.0;
-  for (int c = 0; c < H; ++c) {
-    double s = 0.0;
-    for (int i = 0; i < D; ++i) s = fmax(s, fabs((double)img[WideParams<D, H>::o_W3 + (size_t)i * H + c]));
-    w3max = fmax(w3max, s);
-  }
-  int esh = 7;
-  if (w3max > 0.0 && std::isfinite(w3max)) {
-    int ex;
-    frexp(w3max, &ex);                       // w3max < 2^ex
-    esh = 15 - 8 - ex;
-  }
-  esh = esh > 60 ? 60 : (esh < -60 ? -60 : esh);
+  for (int c = 0; c < H; ++c)
+    for (int i = 0; i < D; ++i) w3max = fmax(w3max, fabs((double)img[WideParams<D, H>::o_W3 + (size_t)i * H + c]));
   cudaError_t e = cudaMemcpyAsync(params_dev, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice, stream);
   if (e != cudaSuccess) return (int)e;
   if ((e = cudaMemcpyAsync(image_dev, w1.data(), umma_image_bytes<H>(), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return (int)e;
   if ((e = cudaMemcpyAsync(scratch + S::o_img2, w2.data(), umma_image_bytes<H>(), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return (int)e;
   if ((e = cudaMemsetAsync(scratch + S::o_ctl, 0, S::o_img2, stream)) != cudaSuccess) return (int)e;
   if ((e = cudaMemsetAsync(scratch + S::o_partial, 0, S::partial_bytes(n_prod, n_cons), stream)) != cudaSuccess) return (int)e;
-  return fast ? launch_bwd_umma_variant<D, H, true>(params_dev, image_dev, args, scale, grad, scratch, n_prod, n_cons, esh, stream)
-              : launch_bwd_umma_variant<D, H, false>(params_dev, image_dev, args, scale, grad, scratch, n_prod, n_cons, esh, stream);
+  return fast ? launch_bwd_umma_variant<D, H, true>(params_dev, image_dev, args, scale, grad, scratch, n_prod, n_cons, (float)w3max, stream)
+              : launch_bwd_umma_variant<D, H, false>(params_dev, image_dev, args, scale, grad, scratch, n_prod, n_cons, (float)w3max, stream);
 }
 
 }  // namespace rlsde
