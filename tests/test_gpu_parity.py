@@ -849,6 +849,36 @@ def test_table_quadrature_path_against_exact_cdf_path(alpha, beta, dt, h):
     assert torch.equal(slab, fast[37:211])
 
 
+@pytest.mark.parametrize("na,base_off", [(24, 0), (25, 0), (26, 0), (27, 0), (25, 1), (27, 3), (26, 1)])
+def test_table_row_classes_for_every_row_length_and_base_alignment(na, base_off):
+    """The quadrature kernel walks rows in residue classes (4 for an odd row length Ns x Na, 2 for 2 mod 4, 1 for 0 mod 4)
+    and shifts each class's column tiles so that stores are 32-byte aligned; the shift depends on the row length, on the
+    slab's first row and on where the output starts.  Every combination against the erf/erfc kernel (plain column tiles),
+    incl. outputs that start 8 and 24 bytes past a 32-byte boundary, and slabs that start inside a class period."""
+    from rl_sde_is_b200.dynamic_programming import compute_p_tensor_batch
+    from rl_sde_is_b200.environments import DoubleWellStoppingTime1D
+    env = DoubleWellStoppingTime1D(beta=1.0, alpha=5.0, dt=0.005)
+    env.set_action_space_bounds()
+    env.discretize_state_space(0.016)                                       # 251 states: cell width 0.16 sd
+    env.action_space_h = -3.0 + 0.25 * np.arange(na)
+    env.n_actions = na
+    env.h_action = 0.25
+    ns = env.n_states
+    assert ns % 2 == 1 and (ns * na) % 4 == {24: 0, 25: 3, 26: 2, 27: 1}[na]
+    exact = compute_p_tensor_batch(env, device_out=True, exact_cdf=True)
+    buf = torch.full((ns * ns * na + 8,), float("nan"), dtype=torch.float64, device="cuda")
+    out = buf[base_off:base_off + ns * ns * na].view(ns, ns, na)
+    fast = compute_p_tensor_batch(env, out=out)
+    assert fast.data_ptr() == out.data_ptr() and float((fast - exact).abs().max()) < 1e-13
+    assert torch.isnan(buf[:base_off]).all() and torch.isnan(buf[base_off + ns * ns * na:]).all()      # nothing outside
+    for lo, hi in ((0, ns), (1, 2), (37, 211), (38, 39), (250, 251), (3, 250)):
+        sbuf = torch.full(((hi - lo) * ns * na + 8,), float("nan"), dtype=torch.float64, device="cuda")
+        sout = sbuf[base_off:base_off + (hi - lo) * ns * na].view(hi - lo, ns, na)
+        slab = compute_p_tensor_batch(env, out=sout, sprime_range=(lo, hi))
+        assert torch.equal(slab, fast[lo:hi]), (lo, hi)
+        assert torch.isnan(sbuf[:base_off]).all() and torch.isnan(sbuf[base_off + (hi - lo) * ns * na:]).all()
+
+
 # ------------------------------------------------------------------------------ tensor-core reverse pass
 @pytest.mark.parametrize("d,ckpt,K", [(1, 1, 6000), (1, 8, 6000), (2, 1, 6000), (3, 4, 6000), (10, 16, 6000), (10, 4, 40000), (4, 2, 40000)])
 def test_reverse_pass_tensor_core_kernel_matches_cuda_core_kernel(d, ckpt, K):
