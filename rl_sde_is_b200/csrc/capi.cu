@@ -56,6 +56,7 @@ static int cuda_fail(cudaError_t e, const char* where) {
 #define RLSDE_SHAPES(X) X(1, 32) X(2, 32) X(3, 32) X(4, 32) X(10, 32)
 #define RLSDE_WIDE_SHAPES(X) X(1, 64) X(1, 128) X(1, 256) X(2, 64) X(2, 128) X(2, 256)
 #define RLSDE_UMMA_SHAPES(X) X(1, 128) X(1, 256) X(2, 128) X(2, 256)
+#define RLSDE_UMMA_FWD_SHAPES(X) X(1, 64) X(2, 64) RLSDE_UMMA_SHAPES(X)      /* forward only: width 64 with resident weights */
 #define RLSDE_UMMA_NARROW_SHAPES(X) X(1, 32) X(2, 32) X(3, 32) X(4, 32) X(10, 32)
 
 static bool shape_is_wide(int d, int H) {
@@ -287,16 +288,16 @@ static int rollout_fwd_impl(const rlsde_env* env, const rlsde_mlp* mlp, const fl
     // wide policies: one kernel family (tiles of trajectories per block), no transition stream, no time slices
     if (tr.base) return RLSDE_ERR_UNSUPPORTED;
     if (workspace_bytes < ws_fixed_bytes()) return RLSDE_ERR_WORKSPACE;
-    // hidden width 128 / 256 with enough trajectories for 128-row tiles on at least half the SMs: the tcgen05 kernel
-    // (rollout_umma.cuh); otherwise -- and always at width 64 -- the CUDA-core tile kernel (rollout_wide.cuh).
+    // hidden width 64 / 128 / 256 with enough trajectories for 128-row tiles on at least half the SMs: the tcgen05 kernel
+    // (rollout_umma.cuh; weights resident at width 64, streamed above); otherwise the CUDA-core tile kernel (rollout_wide.cuh).
     // cfg.wide_kernel: 1 forces tcgen05, 2 forces the CUDA-core kernel.
-    const bool umma_shape = mlp->d_hidden == 128 || mlp->d_hidden == 256;
+    const bool umma_shape = mlp->d_hidden == 64 || mlp->d_hidden == 128 || mlp->d_hidden == 256;
     const bool use_umma = umma_shape && (cfg->wide_kernel == 1 || (cfg->wide_kernel == 0 && A.K >= (long long)sm * UMMA_M / 2));
     if (use_umma) {
 #define X(D_, H_)                                                                                                          \
   if (env->d == D_ && mlp->d_hidden == H_)                                                                                 \
     lrc = launch_rollout_fwd_umma<D_, H_>(params_host, ws_wide_params(workspace_dev), ws_umma_image(workspace_dev), A, sm, stream);
-      RLSDE_UMMA_SHAPES(X)
+      RLSDE_UMMA_FWD_SHAPES(X)
 #undef X
     } else {
 #define X(D_, H_) \

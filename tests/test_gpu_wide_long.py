@@ -270,7 +270,7 @@ def test_hjb_psi_lies_inside_the_importance_sampling_estimate():
 
 
 # ------------------------------------------------------------------------------ tcgen05 forward kernel (rollout_umma.cuh)
-@pytest.mark.parametrize("prefix", ["th128_", "th256_", "t2d_h128_", "tinit_h256_"])
+@pytest.mark.parametrize("prefix", ["th64_", "th128_", "th256_", "t2d_h128_", "tinit_h256_"])
 def test_tcgen05_forward_matches_reference(golden, monkeypatch, prefix):
     """The tensor-core forward kernel (float16 hi/lo operand split, fp32 accumulation in tensor memory) on the reference's
     recorded noise: hit passes exact, returns / loss within 1e-5, and -- since the reverse pass reads its checkpoints -- the
@@ -280,14 +280,14 @@ def test_tcgen05_forward_matches_reference(golden, monkeypatch, prefix):
     _check_torch_case(g, prefix, g[prefix + "noise"])
 
 
-@pytest.mark.parametrize("prefix", ["nh128_", "nh256_"])
+@pytest.mark.parametrize("prefix", ["nh64_", "nh128_", "nh256_"])
 def test_tcgen05_forward_numpy_path_matches_reference(golden, monkeypatch, prefix):
     monkeypatch.setenv("RLSDE_WIDE_KERNEL", "umma")
     g = golden("rollout_wide")
     _check_numpy_case(g, prefix, g[prefix + "noise"])
 
 
-@pytest.mark.parametrize("H", [128, 256])
+@pytest.mark.parametrize("H", [64, 128, 256])
 def test_tcgen05_forward_agrees_with_cuda_core_kernel(H):
     """Same Philox stream through both wide forward kernels (tiles of 128 on the tensor cores / tiles of 32 on the CUDA
     cores): the policies are evaluated to fp32-level accuracy by both, so almost every trajectory hits on the same pass with
