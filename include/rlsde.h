@@ -127,7 +127,7 @@ typedef struct rlsde_rollout_cfg {
   int32_t bwd_kernel;           /* thread-per-trajectory reverse pass, hidden width 32: 0 = automatic (tensor-core kernel),
                                    1 = tensor-core kernel (mma.sync, float16 x 3 split), 2 = CUDA-core kernel (FFMA2) */
   int32_t wide_kernel;          /* forward rollout (hidden width 64 / 128 / 256) and reverse pass (128 / 256): 0 = automatic (tcgen05
-                                   kernels for batches of at least 64 x SMs trajectories; the reverse pass also needs a
+                                   kernels for batches of at least 512 trajectories at width 256, 64 x SMs below; the reverse pass also needs a
                                    workspace of rlsde_workspace_bytes_bwd), 1 = tcgen05 kernels, 2 = CUDA-core tile kernels */
 } rlsde_rollout_cfg;
 

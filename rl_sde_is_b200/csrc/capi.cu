@@ -66,6 +66,12 @@ static bool shape_is_wide(int d, int H) {
   return false;
 }
 
+// smallest batch the tcgen05 tile kernels take automatically.  They advance 128-trajectory tiles at ~13 us (forward) /
+// ~23 us (reverse) per pass at H = 256 whatever the batch, the CUDA-core tile kernels 16-trajectory tiles at ~15 / ~40 us:
+// measured at H = 256, K = 1 000: forward 13.2 against 14.9 ms, reverse 34.9 against 61.8 ms (K = 4 000: 13.2 / 22.4 and 35.7 /
+// 68.4).  At H = 128 the CUDA-core kernels are as fast up to a few thousand trajectories (K = 1 000: 4.7 against 6.3 ms).
+static long long umma_min_k(int H, int sm) { return H >= 256 ? 4 * UMMA_M : (long long)sm * UMMA_M / 2; }
+
 static bool shape_supported(int d, int H, int n_hidden) {
   if (n_hidden != 2) return false;
 #define X(D_, H_) if (d == D_ && H == H_) return true;
@@ -288,11 +294,11 @@ static int rollout_fwd_impl(const rlsde_env* env, const rlsde_mlp* mlp, const fl
     // wide policies: one kernel family (tiles of trajectories per block), no transition stream, no time slices
     if (tr.base) return RLSDE_ERR_UNSUPPORTED;
     if (workspace_bytes < ws_fixed_bytes()) return RLSDE_ERR_WORKSPACE;
-    // hidden width 64 / 128 / 256 with enough trajectories for 128-row tiles on at least half the SMs: the tcgen05 kernel
+    // hidden width 64 / 128 / 256 with enough trajectories (umma_min_k: four 128-row tiles at H = 256, half the SMs below): the tcgen05 kernel
     // (rollout_umma.cuh; weights resident at width 64, streamed above); otherwise the CUDA-core tile kernel (rollout_wide.cuh).
     // cfg.wide_kernel: 1 forces tcgen05, 2 forces the CUDA-core kernel.
     const bool umma_shape = mlp->d_hidden == 64 || mlp->d_hidden == 128 || mlp->d_hidden == 256;
-    const bool use_umma = umma_shape && (cfg->wide_kernel == 1 || (cfg->wide_kernel == 0 && A.K >= (long long)sm * UMMA_M / 2));
+    const bool use_umma = umma_shape && (cfg->wide_kernel == 1 || (cfg->wide_kernel == 0 && A.K >= umma_min_k(mlp->d_hidden, sm)));
     if (use_umma) {
 #define X(D_, H_)                                                                                                          \
   if (env->d == D_ && mlp->d_hidden == H_)                                                                                 \
@@ -453,13 +459,13 @@ int rlsde_rollout_bwd(const rlsde_env* env, const rlsde_mlp* mlp, const float* p
   int lrc = -1;
   if (shape_is_wide(env->d, mlp->d_hidden)) {
     if (A.ckpt_every != 1) return RLSDE_ERR_UNSUPPORTED;        // the wide reverse kernel reads every state from the path
-    // hidden width 128 / 256 with enough trajectories for 128-row tiles on at least half the SMs: the tcgen05 kernel
+    // hidden width 128 / 256 with enough trajectories (umma_min_k): the tcgen05 kernel
     // (rollout_umma_bwd.cuh), given a workspace from rlsde_workspace_bytes_bwd; cfg.wide_kernel as in the forward rollout
     const bool umma_shape = mlp->d_hidden == 128 || mlp->d_hidden == 256;
     const size_t umma_need = umma_shape ? ws_fixed_bytes() + bwd_umma_scratch(env->d, mlp->d_hidden, sm) : 0;
     if (umma_shape && cfg->wide_kernel == 1 && workspace_bytes < umma_need) return RLSDE_ERR_WORKSPACE;
     if (umma_shape && workspace_bytes >= umma_need &&
-        (cfg->wide_kernel == 1 || (cfg->wide_kernel == 0 && A.K >= (long long)sm * UMMA_M / 2))) {
+        (cfg->wide_kernel == 1 || (cfg->wide_kernel == 0 && A.K >= umma_min_k(mlp->d_hidden, sm)))) {
       uint8_t* scratch = (uint8_t*)workspace_dev + ws_fixed_bytes();
 #define X(D_, H_)                                                                                                        \
   if (env->d == D_ && mlp->d_hidden == H_)                                                                               \

@@ -93,10 +93,11 @@ def test_wide_policy_supported_shapes_and_rng_consistency():
     env_c, mlp_c = R.env_struct(env, L.HIT_ALL_GE_LB), L.make_mlp(1, 256)
     n_sm = torch.cuda.get_device_properties(0).multi_processor_count
     K = 32 * n_sm + 77                                       # 32-row tiles
-    big = R.rollout_forward(env_c, mlp_c, params, K, seed=9, n_steps_lim=3000)
+    ffma = {"wide_kernel": "ffma"}                           # (from 512 trajectories the automatic choice at H = 256 is the tcgen05 kernel)
+    big = R.rollout_forward(env_c, mlp_c, params, K, seed=9, n_steps_lim=3000, tuning=ffma)
     assert int(big.stats[L.ST_N_UNFINISHED]) == 0
     k_small = 300                                            # 16-row tiles, shard in the middle of the global batch
-    small = R.rollout_forward(env_c, mlp_c, params, k_small, seed=9, n_steps_lim=3000, traj_offset=1000, K_global=K)
+    small = R.rollout_forward(env_c, mlp_c, params, k_small, seed=9, n_steps_lim=3000, traj_offset=1000, K_global=K, tuning=ffma)
     for a, b in ((big.G[1000:1300], small.G), (big.S[1000:1300], small.S), (big.T[1000:1300], small.T)):
         assert torch.equal(a, b)
     noise = R.noise_fill(9, 64, 1, int(big.T[:64].max().item()) + 1, env.dt)
