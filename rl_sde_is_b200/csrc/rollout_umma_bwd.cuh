@@ -330,6 +330,7 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
 #endif
   unsigned kc = 0;            // running k-step index (A slots and weight stages advance together)
   unsigned pcount = 0;        // running pass index = exchange sequence number
+  unsigned known_consumed = 0;   // thread 0: passes the consumer is known to have taken
   const long long n_tiles = (A.K + UMMA_M - 1) / UMMA_M;
 
   // tiles (length-sorted by the caller) are dealt out boustrophedon: round r goes p = 0 .. n_prod-1 when r is even and
@@ -374,8 +375,10 @@ rollout_bwd_umma_kernel(const float* __restrict__ Wp, const uint8_t* __restrict_
         const uint32_t par = pcount & 1u;
         UB_T(7);
         // ---- the exchange slot of this pass must have been consumed
-        if (tid == 0 && pcount >= (unsigned)UB_RING) {
-          while (ld_acquire(pc + 1) + (unsigned)UB_RING <= pcount) __nanosleep(32);
+        // (thread 0 remembers the last count it read: the acquire load is an L2 round trip, and a count read k passes ago
+        // usually still proves the slot free)
+        if (tid == 0 && known_consumed + (unsigned)UB_RING <= pcount) {
+          while ((known_consumed = ld_acquire(pc + 1)) + (unsigned)UB_RING <= pcount) __nanosleep(32);
         }
         bar_owners();
         UB_T(0);
