@@ -167,3 +167,25 @@ def test_packed_allreduce_two_ranks_gloo():
     ids = np.arange(K_global, dtype=np.float64)
     for _, _, _, g, n, sg in res:
         assert g[2] == K_global and abs(g[0] - ids.sum()) < 1e-3 and n == K_global and sg == ids.sum()
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs without a GPU (it is the CPU arm) and prints one JSON line with the contract's keys."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-trajectories", "200"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["higher_is_better"] is True and line["value"] > 0
+    for key in ("metric", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_tools_and_bench_compile():
+    import glob, py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f in [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")] + glob.glob(os.path.join(root, "tools", "*.py")):
+        py_compile.compile(f, doraise=True)
