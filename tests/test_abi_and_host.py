@@ -189,3 +189,78 @@ def test_tools_and_bench_compile():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for f in [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")] + glob.glob(os.path.join(root, "tools", "*.py")):
         py_compile.compile(f, doraise=True)
+
+
+def test_table_row_class_indexing_covers_every_entry_exactly_once():
+    """Index arithmetic of the quadrature table kernel (csrc/tables.cu: row residue classes, column tiles shifted to 32-byte
+    boundaries, chunks capped in steps and in standard deviations), restated in Python: for many shapes, slabs and output
+    alignments every (row, column) of the slab is produced exactly once, nothing outside, and every warp's first store address is a
+    multiple of 32 bytes."""
+    rng = np.random.default_rng(7)
+    GL_ANCHOR, GL_SPAN_SD = 64, 21.0
+    for trial in range(60):
+        Ns, Na = int(rng.integers(2, 70)), int(rng.integers(1, 40))
+        sp_begin = int(rng.integers(0, Ns))
+        sp_end = int(rng.integers(sp_begin + 1, Ns + 1))
+        base = int(rng.integers(0, 4))                     # output pointer in doubles modulo 4
+        step_sd0 = float(rng.choice([0.05, 0.1, 0.2]))
+        cols = Ns * Na
+        Q = 1 if cols % 4 == 0 else (2 if cols % 2 == 0 else 4)
+        rows_per_class = (Ns + Q - 1) // Q
+        steps_cap = int(GL_SPAN_SD / (Q * step_sd0))
+        steps_cap = max(1, min(GL_ANCHOR, steps_cap))
+        n_chunks_full = (rows_per_class + steps_cap - 1) // steps_cap
+        steps = (rows_per_class + n_chunks_full - 1) // n_chunks_full
+        kc_lo = ((sp_begin - (Q - 1)) // Q if sp_begin >= Q else 0) // steps
+        kc_hi = ((sp_end - 1) // Q) // steps
+        grid_x, grid_y = (cols + 3 + 127) // 128, (kc_hi - kc_lo + 1) * Q
+        hits = np.zeros((sp_end - sp_begin, cols), dtype=np.int32)
+        for by in range(grid_y):
+            j, kc = by % Q, kc_lo + by // Q
+            rel = (((j - sp_begin) % 4 + 4) % 4) * (cols & 3)
+            shift = (base + rel) & 3
+            r0 = Q * kc * steps + j
+            if r0 >= sp_end:
+                continue
+            i_lo = 0 if r0 >= sp_begin else (sp_begin - r0 + Q - 1) // Q
+            i_hi = min(steps, (sp_end - r0 + Q - 1) // Q)
+            if i_lo >= i_hi:
+                continue
+            rows = r0 + Q * np.arange(i_lo, i_hi)
+            assert rows.min() >= sp_begin and rows.max() < sp_end
+            for bx in range(grid_x):
+                c = bx * 128 + np.arange(128) - shift
+                for w in range(4):                         # first lane of each warp: address multiple of 4 doubles on every row
+                    c0 = bx * 128 + 32 * w - shift
+                    assert all((base + (r - sp_begin) * cols + c0) % 4 == 0 for r in rows)
+                c = c[(c >= 0) & (c < cols)]
+                hits[np.ix_(rows - sp_begin, c)] += 1
+        assert (hits == 1).all(), (Ns, Na, sp_begin, sp_end, base)
+
+
+def test_tcgen05_reverse_pass_work_assignment():
+    """Static work assignment of the producer / consumer reverse kernel (csrc/rollout_umma_bwd*.cuh), restated: every
+    128-trajectory tile goes to exactly one producer (boustrophedon deal), every producer is polled by exactly one consumer,
+    and the grid fits the SMs (the launch is cooperative)."""
+    UMMA_M, PPC = 128, 2
+    for sm in (148, 132, 16, 3):
+        for K in (1, 127, 128, 129, 1000, 9472, 60000, 10**6):
+            tiles = (K + UMMA_M - 1) // UMMA_M
+            n_prod = max(1, min(tiles, sm * PPC // (PPC + 1)))
+            n_cons = (n_prod + PPC - 1) // PPC
+            assert n_prod + n_cons <= max(sm, 2)
+            seen = np.zeros(tiles, dtype=np.int32)
+            for p in range(n_prod):
+                rnd = 0
+                while rnd * n_prod < tiles:
+                    t = rnd * n_prod + ((n_prod - 1 - p) if (rnd & 1) else p)
+                    if t < tiles:
+                        seen[t] += 1
+                    rnd += 1
+            assert (seen == 1).all(), (sm, K)
+            polled = np.zeros(n_prod, dtype=np.int32)
+            for c in range(n_cons):
+                for i in range(PPC):
+                    if c + i * n_cons < n_prod:
+                        polled[c + i * n_cons] += 1
+            assert (polled == 1).all(), (sm, K)
